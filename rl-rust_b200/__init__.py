@@ -1,0 +1,17 @@
+"""rl-rust_b200 — B200-native batched tabular-RL engine behind the trait surface of
+JohnVithor/RL-Rust's hot path (Env / Agent / Policy / ActionSelection).
+
+The package holds only what that path needs: `csrc/` (hand-written sm_100a kernels + the
+C ABI of include/rlb.h, built into librlb.so), `_abi.py` (ctypes binding) and `api.py`
+(host-side mirror of the reference's interface).  Import it with
+`importlib.import_module("rl-rust_b200")` (the directory name is not a Python identifier).
+"""
+from . import _abi as abi
+from ._abi import Engine, EnvNotReady, RlbError
+from .api import (BlackJackEnv, CliffWalkingEnv, DoubleTabularPolicy, ElegibilityTracesAgent, Env, FrozenLakeEnv,
+                  OneStepAgent, TabularPolicy, TaxiEnv, UniformEpsilonGreed, UpperConfidenceBound, expected_sarsa,
+                  qlearning, sarsa)
+
+__all__ = ["abi", "Engine", "EnvNotReady", "RlbError", "BlackJackEnv", "CliffWalkingEnv", "DoubleTabularPolicy",
+           "ElegibilityTracesAgent", "Env", "FrozenLakeEnv", "OneStepAgent", "TabularPolicy", "TaxiEnv",
+           "UniformEpsilonGreed", "UpperConfidenceBound", "expected_sarsa", "qlearning", "sarsa"]

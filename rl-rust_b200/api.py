@@ -1,0 +1,295 @@
+"""Host-side mirror of the reference's trait surface for the hot path, over the C ABI.
+
+Same names, argument order and error behaviour as JohnVithor/RL-Rust (paths below are under
+its `src/`), batched: every object stands for `n_agents` independent reference objects, each
+on its own Philox stream.  n_agents = 1 is the reference's single trait object.
+
+    env    = TaxiEnv(100)                                         # env/taxi.rs:57
+    policy = TabularPolicy(0.05, 0.0)                             # policy/tabular_policy.rs:15
+    sel    = UniformEpsilonGreed(1.0, ("sub", 2e-5), 0.0)         # action_selection/uniform_epsilon_greed.rs:31
+    agent  = OneStepAgent(policy, 0.95, sel, qlearning,           # agent/one_step_agent.rs:16
+                          n_agents=1 << 20, seed=7)
+    rewards, lengths, errors = agent.train(env, 100000, 10000)    # agent.rs:66-118
+
+The Rust closure `epsilon_decay: Rc<dyn Fn(f64)->f64>` cannot run on the device; it is given
+as ("sub", k) for `|a| a - k` (bin/taxi.rs:132) or ("mul", k) for `|a| a * k`
+(bin/frozen_lake_neural.rs:181).
+"""
+import numpy as np
+
+from . import _abi as abi
+
+# agent.rs:19-45 — the three GetNextQValue functions are passed by name
+sarsa = abi.TARGET_SARSA
+qlearning = abi.TARGET_QLEARNING
+expected_sarsa = abi.TARGET_EXPECTED_SARSA
+
+EnvNotReady = abi.EnvNotReady
+
+
+# --------------------------------------------------------------------------- Env<T, COUNT>
+class Env:
+    """env.rs:19-49.  `reset`/`step` act on all agents of the engine the env is bound to; an
+    env is bound by the first agent that trains on it (or by `bind`)."""
+    kind = None
+    COUNT = 0
+    ACTIONS = ()
+
+    def __init__(self):
+        self._engine = None
+
+    def action_size(self):          # env.rs:20-22
+        return self.COUNT
+
+    def _cfg(self):
+        return {}
+
+    def bind(self, engine):
+        self._engine = engine
+        return self
+
+    def reset(self):                # env.rs:23
+        if self._engine is None:
+            raise RuntimeError("env is not bound to an engine yet (train an agent on it, or call bind())")
+        return self._engine.env_reset()
+
+    def step(self, action):         # env.rs:24 — raises EnvNotReady where the reference returns Err(EnvNotReady)
+        if self._engine is None:
+            raise RuntimeError("env is not bound to an engine yet")
+        a = np.broadcast_to(np.asarray(action, np.uint32), (self._engine.N,))
+        return self._engine.env_step(a)
+
+    def get_action_label(self, action):   # env.rs:48
+        return self.ACTIONS[action]
+
+
+class BlackJackEnv(Env):
+    """env/blackjack.rs:30-163.  Observations are dense indices here; `obs_id` gives the
+    reference's fxhash id (blackjack.rs:25-27)."""
+    kind = abi.ENV_BLACKJACK
+    COUNT = 2
+    ACTIONS = ("HIT", "STICK")
+
+    @staticmethod
+    def obs_id(dense_index):
+        return abi.blackjack_obs_id(int(dense_index))
+
+    @staticmethod
+    def dense_index(obs_id):
+        return abi.blackjack_dense_index(int(obs_id))
+
+
+class FrozenLakeEnv(Env):
+    """env/frozen_lake.rs:12-134.  `map` is FrozenLakeEnv.MAP_4X4 or MAP_8X8."""
+    kind = abi.ENV_FROZEN_LAKE
+    COUNT = 4
+    ACTIONS = ("LEFT", "DOWN", "RIGHT", "UP")
+    MAP_4X4 = ("SFFF", "FHFH", "FFFH", "HFFG")
+    MAP_8X8 = ("SFFFFFFF", "FFFFFFFF", "FFFHFFFF", "FFFFFHFF", "FFFHFFFF", "FHHFFFHF", "FHFFHFHF", "FFFHFFFG")
+
+    def __init__(self, map, is_slippery, max_steps):
+        super().__init__()
+        map = tuple(map)
+        if map == self.MAP_4X4:
+            self.map_id = 0
+        elif map == self.MAP_8X8:
+            self.map_id = 1
+        else:
+            raise ValueError("only the reference's MAP_4X4 / MAP_8X8 are supported")
+        self.is_slippery = bool(is_slippery)
+        self.max_steps = int(max_steps)
+
+    def _cfg(self):
+        return dict(map_id=self.map_id, slippery=self.is_slippery, max_steps=self.max_steps)
+
+
+class CliffWalkingEnv(Env):
+    """env/cliff_walking.rs:6-89"""
+    kind = abi.ENV_CLIFF_WALKING
+    COUNT = 4
+    ACTIONS = ("LEFT", "DOWN", "RIGHT", "UP")
+
+    def __init__(self, max_steps):
+        super().__init__()
+        self.max_steps = int(max_steps)
+
+    def _cfg(self):
+        return dict(max_steps=self.max_steps)
+
+
+class TaxiEnv(Env):
+    """env/taxi.rs:10-159"""
+    kind = abi.ENV_TAXI
+    COUNT = 6
+    ACTIONS = ("DOWN", "UP", "RIGHT", "LEFT", "PICKUP", "DROPOFF")
+
+    def __init__(self, max_steps):
+        super().__init__()
+        self.max_steps = int(max_steps)
+
+    def _cfg(self):
+        return dict(max_steps=self.max_steps)
+
+    @staticmethod
+    def decode(i):                  # taxi.rs:44-55
+        return (i // 100, (i // 20) % 5, (i // 4) % 5, i % 4)
+
+
+# --------------------------------------------------------------------------- Policy<T, COUNT>
+class TabularPolicy:
+    """policy/tabular_policy.rs:8-44 ("Basic")"""
+    kind = abi.POLICY_BASIC
+
+    def __init__(self, learning_rate, default_value):
+        self.learning_rate = float(learning_rate)
+        self.default_value = float(default_value)
+
+
+class DoubleTabularPolicy(TabularPolicy):
+    """policy/double_tabular_policy.rs:8-67"""
+    kind = abi.POLICY_DOUBLE
+
+
+# --------------------------------------------------------------------------- ActionSelection<T, COUNT>
+class UniformEpsilonGreed:
+    """action_selection/uniform_epsilon_greed.rs:8-80"""
+    kind = abi.SEL_EPS_GREEDY
+
+    def __init__(self, epsilon, epsilon_decay, final_epsilon):
+        op, k = epsilon_decay
+        if op not in ("sub", "mul"):
+            raise ValueError("epsilon_decay must be ('sub', k) or ('mul', k)")
+        self.initial_epsilon = float(epsilon)
+        self.decay_kind = abi.DECAY_SUB if op == "sub" else abi.DECAY_MUL
+        self.decay_param = float(k)
+        self.final_epsilon = float(final_epsilon)
+
+
+class UpperConfidenceBound:
+    """action_selection/upper_confidence_bound.rs:9-68"""
+    kind = abi.SEL_UCB
+
+    def __init__(self, confidence_level):
+        self.confidence_level = float(confidence_level)
+
+
+# --------------------------------------------------------------------------- Agent<T, COUNT>
+class _Agent:
+    agent_kind = None
+
+    def __init__(self, policy, discount_factor, action_selection, lambda_factor, get_next_q_value, *, n_agents=1,
+                 seed=0x5EED0001, first_agent_id=0, real="f32", device=0):
+        self.policy = policy
+        self.discount_factor = float(discount_factor)
+        self.lambda_factor = float(lambda_factor)
+        self._selectors = {}
+        self._remember(action_selection)
+        self.selector_kind = action_selection.kind
+        self.get_next_q_value = get_next_q_value
+        self.n_agents, self.seed, self.first_agent_id, self.device = int(n_agents), int(seed), int(first_agent_id), device
+        self.real = abi.REAL_F32 if real in ("f32", abi.REAL_F32) else abi.REAL_F64
+        self.engine = None
+
+    def _remember(self, sel):
+        self._selectors[sel.kind] = sel
+
+    def _bind(self, env):
+        if self.engine is not None:
+            if env._engine is not self.engine:
+                raise RuntimeError("agent is already bound to another env")
+            return
+        eg = self._selectors.get(abi.SEL_EPS_GREEDY)
+        ucb = self._selectors.get(abi.SEL_UCB)
+        kw = dict(n_agents=self.n_agents, policy=self.policy.kind, selector=self.selector_kind,
+                  target=self.get_next_q_value, agent=self.agent_kind, real=self.real,
+                  learning_rate=self.policy.learning_rate, default_value=self.policy.default_value,
+                  discount_factor=self.discount_factor, lambda_factor=self.lambda_factor, seed=self.seed,
+                  first_agent_id=self.first_agent_id, device=self.device)
+        if eg is not None:
+            kw.update(initial_epsilon=eg.initial_epsilon, decay_kind=eg.decay_kind, epsilon_decay=eg.decay_param,
+                      final_epsilon=eg.final_epsilon)
+        if ucb is not None:
+            kw.update(confidence_level=ucb.confidence_level)
+        kw.update(env._cfg())
+        self.engine = abi.Engine(env.kind, **kw)
+        env.bind(self.engine)
+
+    # agent.rs:48
+    def set_future_q_value_func(self, func):
+        self.get_next_q_value = func
+        if self.engine is not None:
+            self.engine.set_target(func)
+
+    # agent.rs:50 — the engine holds one parameter set per selector kind, fixed at bind time
+    def set_action_selector(self, action_selector):
+        if self.engine is not None and action_selector.kind not in self._selectors:
+            raise RuntimeError("selector parameters must be known before the agent is bound; pass every selector "
+                               "you will use to register_selector() first")
+        self._remember(action_selector)
+        self.selector_kind = action_selector.kind
+        if self.engine is not None:
+            self.engine.set_selector(action_selector.kind)
+
+    def register_selector(self, action_selector):
+        """Make a selector's parameters known before binding (the CLI builds both up front, bin/taxi.rs:129-136)."""
+        if self.engine is not None:
+            raise RuntimeError("agent already bound")
+        self._remember(action_selector)
+
+    def get_action(self, obs):      # agent.rs:52
+        return self.engine.get_action(obs)
+
+    def update(self, curr_obs, curr_action, reward, terminated, next_obs, next_action):   # agent.rs:54-62
+        return self.engine.update(curr_obs, curr_action, reward, terminated, next_obs, next_action)
+
+    def reset(self):                # agent.rs:64
+        if self.engine is not None:
+            self.engine.agent_reset()
+
+    def train(self, env, n_episodes, eval_at, *, raw=False):
+        """agent.rs:66-118.  Returns (reward_history, episode_length, training_error).
+
+        With n_agents == 1 these are the reference's three vectors exactly (training_error
+        per step).  With more agents, reward_history and episode_length are [n_agents,
+        n_episodes] arrays and training_error is the per-episode sum of TDs [n_agents,
+        n_episodes] (a per-step stream for millions of agents does not fit anywhere).
+        raw=True returns the engine's dict instead (per-episode sums over agents, counters).
+        """
+        if eval_at == 0:
+            raise ZeroDivisionError("attempt to calculate the remainder with a divisor of zero")   # agent.rs:107
+        self._bind(env)
+        if raw:
+            return self.engine.train(n_episodes, eval_at)
+        if self.n_agents == 1:
+            cap = 0
+            res = self.engine.train(n_episodes, eval_at, sums=False, episodes=True)
+            ep = res["episodes"][:, 0]
+            return ep["ret"].astype(np.float64), ep["length"].astype(np.uint64), ep["td_sum"].astype(np.float64)
+        res = self.engine.train(n_episodes, eval_at, sums=False, episodes=True)
+        ep = res["episodes"]
+        return (ep["ret"].T.astype(np.float64), ep["length"].T.astype(np.uint64), ep["td_sum"].T.astype(np.float64))
+
+    def evaluate(self, env, n_episodes):
+        """agent.rs:120-141.  Returns (reward_history, episode_length)."""
+        self._bind(env)
+        res = self.engine.evaluate(n_episodes, sums=False, episodes=True)
+        ep = res["episodes"]
+        if self.n_agents == 1:
+            return ep["ret"][:, 0].astype(np.float64), ep["length"][:, 0].astype(np.uint64)
+        return ep["ret"].T.astype(np.float64), ep["length"].T.astype(np.uint64)
+
+
+class OneStepAgent(_Agent):
+    """agent/one_step_agent.rs:7-86"""
+    agent_kind = abi.AGENT_ONE_STEP
+
+    def __init__(self, policy, discount_factor, action_selection, get_next_q_value, **kw):
+        super().__init__(policy, discount_factor, action_selection, 0.0, get_next_q_value, **kw)
+
+
+class ElegibilityTracesAgent(_Agent):
+    """agent/elegibility_traces_agent.rs:8-104"""
+    agent_kind = abi.AGENT_TRACES
+
+    def __init__(self, policy, discount_factor, action_selection, lambda_factor, get_next_q_value, **kw):
+        super().__init__(policy, discount_factor, action_selection, lambda_factor, get_next_q_value, **kw)

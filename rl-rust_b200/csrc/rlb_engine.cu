@@ -1,0 +1,811 @@
+// rlb_engine.cu — engine lifecycle and the C ABI of include/rlb.h.
+//
+// The engine owns every device buffer: per-agent Q tables / UCB counts / eligibility rows
+// in HBM (agent-major, one 32/64-byte-aligned row per state), per-agent scalars (RNG word
+// index, epsilon, UCB t, Double flag, env state) as SoA arrays, the env transition tables,
+// and a scratch ring for the per-episode record stream that k_run writes and
+// k_episode_sums reduces.  There is no CPU path: every compute entry point needs a device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rlb_host.h"
+#include "rlb_launch.h"
+#include "rlb_step_kernels.cuh"
+
+using namespace rlb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+rlb_status cuda_fail(cudaError_t err, const char* what) {
+    set_error("%s: %s", what, cudaGetErrorString(err));
+    return err == cudaErrorMemoryAllocation ? RLB_ERR_OOM : RLB_ERR_CUDA;
+}
+
+#define CK(call)                                                  \
+    do {                                                          \
+        cudaError_t err__ = (call);                               \
+        if (err__ != cudaSuccess) return cuda_fail(err__, #call); \
+    } while (0)
+
+template <int ENV> struct EnvTag {};
+
+}   // namespace
+
+struct rlb_engine {
+    rlb_config cfg;
+    uint32_t S = 0, A = 0, APAD = 0, T = 1;
+    size_t real_size = 4;
+    Variant variant{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DevParams dp{};
+    EnvTables tables;
+    // owned device buffers
+    void* d_q = nullptr; size_t q_bytes = 0;
+    uint32_t* d_counts = nullptr; size_t counts_bytes = 0;
+    void* d_etr = nullptr;
+    uint16_t* d_vis = nullptr;
+    uint32_t* d_nvis = nullptr;
+    uint64_t* d_rng_n = nullptr;
+    double* d_eps = nullptr;
+    uint64_t* d_ucb_t = nullptr;
+    uint8_t* d_flag = nullptr;
+    EnvState* d_env = nullptr;
+    uint16_t* d_trans = nullptr;
+    uint64_t* d_thr = nullptr;
+    uint16_t* d_thr_state = nullptr;
+    unsigned long long* d_totals = nullptr;   // [4]: train steps, eval steps, eval episodes, (double) eval return
+    uint32_t* d_flagword = nullptr;
+    // scratch
+    void* d_episodes = nullptr; size_t episodes_cap = 0;
+    double* d_sums = nullptr; size_t sums_cap = 0;
+    void* d_stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes attr;
+    cudaError_t err = cudaPointerGetAttributes(&attr, p);
+    if (err != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// copy device -> caller buffer (host or device)
+cudaError_t copy_out(rlb_engine* e, void* dst, const void* src_dev, size_t bytes) {
+    if (!dst || !bytes) return cudaSuccess;
+    cudaError_t err = cudaMemcpyAsync(dst, src_dev, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream);
+    if (err != cudaSuccess) return err;
+    return is_device_ptr(dst) ? cudaSuccess : cudaStreamSynchronize(e->stream);
+}
+
+// make caller data (host or device) readable on the device; returns a device pointer
+cudaError_t stage_in(rlb_engine* e, int slot, const void* src, size_t bytes, const void** out) {
+    if (!src) { *out = nullptr; return cudaSuccess; }
+    if (is_device_ptr(src)) { *out = src; return cudaSuccess; }
+    if (e->stage_cap[slot] < bytes) {
+        if (e->d_stage[slot]) cudaFree(e->d_stage[slot]);
+        e->d_stage[slot] = nullptr; e->stage_cap[slot] = 0;
+        cudaError_t err = cudaMalloc(&e->d_stage[slot], bytes);
+        if (err != cudaSuccess) return err;
+        e->stage_cap[slot] = bytes;
+    }
+    cudaError_t err = cudaMemcpyAsync(e->d_stage[slot], src, bytes, cudaMemcpyHostToDevice, e->stream);
+    *out = e->d_stage[slot];
+    return err;
+}
+// device scratch to receive an output that the caller wants on the host (or the caller's own device buffer)
+cudaError_t stage_out(rlb_engine* e, int slot, void* dst, size_t bytes, void** dev) {
+    if (!dst) { *dev = nullptr; return cudaSuccess; }
+    if (is_device_ptr(dst)) { *dev = dst; return cudaSuccess; }
+    if (e->stage_cap[slot] < bytes) {
+        if (e->d_stage[slot]) cudaFree(e->d_stage[slot]);
+        e->d_stage[slot] = nullptr; e->stage_cap[slot] = 0;
+        cudaError_t err = cudaMalloc(&e->d_stage[slot], bytes);
+        if (err != cudaSuccess) return err;
+        e->stage_cap[slot] = bytes;
+    }
+    *dev = e->d_stage[slot];
+    return cudaSuccess;
+}
+cudaError_t finish_out(rlb_engine* e, void* dst, const void* dev, size_t bytes) {
+    if (!dst || dst == dev) return cudaSuccess;
+    return copy_out(e, dst, dev, bytes);
+}
+
+template <typename V>
+cudaError_t fill(rlb_engine* e, V* ptr, uint64_t n, V value) {
+    if (!n) return cudaSuccess;
+    unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148u * 16u);
+    k_fill<V><<<grid, 256, 0, e->stream>>>(ptr, n, value);
+    return cudaGetLastError();
+}
+
+cudaError_t fill_q_default(rlb_engine* e) {
+    const uint64_t n = e->q_bytes / e->real_size;
+    if (e->cfg.real_kind == RLB_REAL_F32) return fill<float>(e, (float*)e->d_q, n, (float)e->cfg.default_value);
+    return fill<double>(e, (double*)e->d_q, n, e->cfg.default_value);
+}
+
+cudaError_t dispatch_run(rlb_engine* e, const DevParams& p) {
+    switch (e->cfg.env_kind) {
+        case RLB_ENV_BLACKJACK: return launch_run<RLB_ENV_BLACKJACK>(e->variant, p, e->stream);
+        case RLB_ENV_FROZEN_LAKE: return launch_run<RLB_ENV_FROZEN_LAKE>(e->variant, p, e->stream);
+        case RLB_ENV_CLIFF_WALKING: return launch_run<RLB_ENV_CLIFF_WALKING>(e->variant, p, e->stream);
+        default: return launch_run<RLB_ENV_TAXI>(e->variant, p, e->stream);
+    }
+}
+cudaError_t dispatch_step(rlb_engine* e, StepOp op, const StepArgs& a) {
+    switch (e->cfg.env_kind) {
+        case RLB_ENV_BLACKJACK: return launch_step<RLB_ENV_BLACKJACK>(op, e->variant, e->dp, a, e->stream);
+        case RLB_ENV_FROZEN_LAKE: return launch_step<RLB_ENV_FROZEN_LAKE>(op, e->variant, e->dp, a, e->stream);
+        case RLB_ENV_CLIFF_WALKING: return launch_step<RLB_ENV_CLIFF_WALKING>(op, e->variant, e->dp, a, e->stream);
+        default: return launch_step<RLB_ENV_TAXI>(op, e->variant, e->dp, a, e->stream);
+    }
+}
+
+// (re)build the selector state: UniformEpsilonGreed::new / UpperConfidenceBound::new
+rlb_status install_selector(rlb_engine* e, int kind) {
+    const uint64_t N = e->cfg.n_agents;
+    e->cfg.selector_kind = kind;
+    e->variant.sel = kind;
+    CK(fill<double>(e, e->d_eps, N, e->cfg.initial_epsilon));
+    CK(fill<uint64_t>(e, e->d_ucb_t, N, 1ull));
+    if (kind == RLB_SEL_UCB) {
+        if (!e->d_counts) {
+            e->counts_bytes = (size_t)N * e->S * e->APAD * sizeof(uint32_t);
+            CK(cudaMalloc(&e->d_counts, e->counts_bytes));
+        }
+        CK(cudaMemsetAsync(e->d_counts, 0, e->counts_bytes, e->stream));
+    }
+    e->dp.counts = e->d_counts;
+    return RLB_OK;
+}
+
+size_t episode_rec_size(const rlb_engine* e) { return e->cfg.real_kind == RLB_REAL_F32 ? sizeof(rlb_episode_f32) : sizeof(rlb_episode_f64); }
+
+rlb_status ensure_episode_scratch(rlb_engine* e, uint64_t episodes) {
+    const size_t need = (size_t)episodes * e->cfg.n_agents * episode_rec_size(e);
+    if (e->episodes_cap < need) {
+        if (e->d_episodes) cudaFree(e->d_episodes);
+        e->d_episodes = nullptr; e->episodes_cap = 0;
+        CK(cudaMalloc(&e->d_episodes, need));
+        e->episodes_cap = need;
+    }
+    const size_t need_s = (size_t)episodes * 4 * sizeof(double);
+    if (e->sums_cap < need_s) {
+        if (e->d_sums) cudaFree(e->d_sums);
+        e->d_sums = nullptr; e->sums_cap = 0;
+        CK(cudaMalloc(&e->d_sums, need_s));
+        e->sums_cap = need_s;
+    }
+    return RLB_OK;
+}
+
+// how many episode indices one launch may cover so that the record stream fits the scratch budget
+uint64_t chunk_episodes(const rlb_engine* e, uint64_t want) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 1ull << 30; }
+    size_t budget = std::min<size_t>((size_t)16 << 30, (free_b + e->episodes_cap) / 3);
+    const size_t per_ep = (size_t)e->cfg.n_agents * episode_rec_size(e);
+    uint64_t chunk = std::max<uint64_t>(1, budget / std::max<size_t>(per_ep, 1));
+    return std::min<uint64_t>(chunk, std::max<uint64_t>(want, 1));
+}
+
+rlb_status reduce_episodes(rlb_engine* e, uint64_t n_ep) {
+    if (!n_ep) return RLB_OK;
+    if (e->cfg.real_kind == RLB_REAL_F32) k_episode_sums<float><<<(unsigned)n_ep, 256, 0, e->stream>>>(e->d_episodes, e->cfg.n_agents, e->d_sums);
+    else k_episode_sums<double><<<(unsigned)n_ep, 256, 0, e->stream>>>(e->d_episodes, e->cfg.n_agents, e->d_sums);
+    CK(cudaGetLastError());
+    return RLB_OK;
+}
+
+bool valid_cfg(const rlb_config* c) {
+    if (!c || c->struct_size != sizeof(rlb_config)) { set_error("rlb_config.struct_size mismatch (got %u, want %zu)", c ? c->struct_size : 0u, sizeof(rlb_config)); return false; }
+    if (c->env_kind < 0 || c->env_kind > 3) { set_error("env_kind out of range"); return false; }
+    if (c->policy_kind < 0 || c->policy_kind > 1 || c->selector_kind < 0 || c->selector_kind > 1 || c->target_kind < 0 ||
+        c->target_kind > 2 || c->agent_kind < 0 || c->agent_kind > 1 || c->real_kind < 0 || c->real_kind > 1 ||
+        c->decay_kind < 0 || c->decay_kind > 1) { set_error("enum field out of range"); return false; }
+    if (c->n_agents == 0) { set_error("n_agents must be > 0"); return false; }
+    if (c->store_kind > 2) { set_error("store_kind out of range"); return false; }
+    return true;
+}
+
+}   // namespace
+
+extern "C" {
+
+int rlb_abi_version(void) { return RLB_ABI_VERSION; }
+const char* rlb_last_error_string(void) { return g_last_error.c_str(); }
+int rlb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
+    if (!out) { set_error("out is NULL"); return RLB_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (!valid_cfg(cfg)) return RLB_ERR_INVALID_ARG;
+    int ndev = 0;
+    cudaError_t derr = cudaGetDeviceCount(&ndev);
+    if (derr != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); librlb has no CPU path", derr == cudaSuccess ? "0 devices" : cudaGetErrorString(derr));
+        return RLB_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("device %d out of range (have %d)", cfg->device, ndev); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(cfg->device));
+
+    rlb_engine* e = new rlb_engine();
+    e->cfg = *cfg;
+    std::string err;
+    if (!build_env_tables(e->cfg, e->tables, err)) { set_error("%s", err.c_str()); delete e; return RLB_ERR_INVALID_ARG; }
+    e->S = e->tables.S;
+    e->A = e->tables.A;
+    e->APAD = e->A == 6 ? 8 : e->A;
+    e->T = cfg->policy_kind == RLB_POLICY_DOUBLE ? 2 : 1;
+    e->real_size = cfg->real_kind == RLB_REAL_F32 ? 4 : 8;
+    e->variant = Variant{cfg->real_kind, cfg->policy_kind, cfg->selector_kind, cfg->agent_kind == RLB_AGENT_TRACES ? 1 : 0};
+    const uint64_t N = cfg->n_agents;
+
+    auto fail = [&](rlb_status st) { rlb_engine_destroy(e); return st; };
+#define CKE(call)                                                          \
+    do {                                                                   \
+        cudaError_t err__ = (call);                                        \
+        if (err__ != cudaSuccess) return fail(cuda_fail(err__, #call));    \
+    } while (0)
+
+    CKE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+    CKE(cudaEventCreate(&e->ev0));
+    CKE(cudaEventCreate(&e->ev1));
+
+    e->q_bytes = (size_t)N * e->S * e->T * e->APAD * e->real_size;
+    CKE(cudaMalloc(&e->d_q, e->q_bytes));
+    uint32_t vmax = 0;
+    if (e->variant.trace) {
+        // distinct states updated in one episode: <= episode length <= max_steps + 1 (truncation pseudo-step), <= S.
+        // Blackjack has no step limit; a hand holds at most 16 cards (blackjack.rs:32-35).
+        uint64_t by_steps = cfg->env_kind == RLB_ENV_BLACKJACK ? 32ull : (uint64_t)cfg->max_steps + 1ull;
+        vmax = (uint32_t)std::min<uint64_t>(e->S, by_steps);
+        CKE(cudaMalloc(&e->d_etr, (size_t)N * vmax * e->APAD * e->real_size));
+        CKE(cudaMalloc(&e->d_vis, (size_t)N * vmax * sizeof(uint16_t)));
+    }
+    CKE(cudaMalloc(&e->d_nvis, N * sizeof(uint32_t)));
+    CKE(cudaMalloc(&e->d_rng_n, N * sizeof(uint64_t)));
+    CKE(cudaMalloc(&e->d_eps, N * sizeof(double)));
+    CKE(cudaMalloc(&e->d_ucb_t, N * sizeof(uint64_t)));
+    CKE(cudaMalloc(&e->d_flag, N * sizeof(uint8_t)));
+    CKE(cudaMalloc(&e->d_env, N * sizeof(EnvState)));
+    CKE(cudaMalloc(&e->d_totals, 4 * sizeof(unsigned long long)));
+    CKE(cudaMalloc(&e->d_flagword, sizeof(uint32_t)));
+    if (!e->tables.trans.empty()) {
+        CKE(cudaMalloc(&e->d_trans, e->tables.trans.size() * sizeof(uint16_t)));
+        CKE(cudaMemcpyAsync(e->d_trans, e->tables.trans.data(), e->tables.trans.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
+    }
+    if (!e->tables.thr.empty()) {
+        CKE(cudaMalloc(&e->d_thr, e->tables.thr.size() * sizeof(uint64_t)));
+        CKE(cudaMalloc(&e->d_thr_state, e->tables.thr_state.size() * sizeof(uint16_t)));
+        CKE(cudaMemcpyAsync(e->d_thr, e->tables.thr.data(), e->tables.thr.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+        CKE(cudaMemcpyAsync(e->d_thr_state, e->tables.thr_state.data(), e->tables.thr_state.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
+    }
+
+    DevParams& p = e->dp;
+    p.q = e->d_q; p.counts = nullptr; p.etr = e->d_etr; p.vis = e->d_vis; p.nvis = e->d_nvis;
+    p.rng_n = e->d_rng_n; p.eps = e->d_eps; p.ucb_t = e->d_ucb_t; p.flag = e->d_flag; p.env = e->d_env;
+    p.trans = e->d_trans; p.thr = e->d_thr; p.thr_state = e->d_thr_state; p.n_thr = (uint32_t)e->tables.thr.size();
+    p.slip_thr0 = e->tables.slip_thr0; p.slip_thr1 = e->tables.slip_thr1; p.slippery = cfg->slippery;
+    p.lr = cfg->learning_rate; p.gamma = cfg->discount_factor; p.lambda = cfg->lambda_factor;
+    p.eps0 = cfg->initial_epsilon; p.eps_decay = cfg->epsilon_decay; p.eps_final = cfg->final_epsilon;
+    p.ucb_c = cfg->confidence_level; p.default_q = cfg->default_value;
+    p.decay_kind = cfg->decay_kind; p.target = cfg->target_kind;
+    p.max_steps = cfg->max_steps; p.S = e->S; p.vmax = vmax;
+    p.seed = cfg->seed; p.first_agent = cfg->first_agent_id; p.n_agents = N;
+    p.mode = 0; p.eval_episodes = 100; p.ep0 = p.ep1 = 0; p.eval_at = 1; p.n_eval = 0;
+    p.episodes = nullptr; p.traj = nullptr; p.traj_cap = 0; p.traj_count = nullptr;
+    p.totals = e->d_totals; p.eval_ret_total = reinterpret_cast<double*>(e->d_totals + 3);
+
+    CKE(fill_q_default(e));
+    CKE(cudaMemsetAsync(e->d_nvis, 0, N * sizeof(uint32_t), e->stream));
+    CKE(cudaMemsetAsync(e->d_rng_n, 0, N * sizeof(uint64_t), e->stream));
+    CKE(fill<uint8_t>(e, e->d_flag, N, (uint8_t)1));   // policy_flag: true (double_tabular_policy.rs:23)
+    rlb_status st = install_selector(e, cfg->selector_kind);
+    if (st != RLB_OK) return fail(st);
+    CKE(dispatch_step(e, OP_ENV_CONSTRUCT, StepArgs()));   // Env::new(): Blackjack deals a hand
+    CKE(cudaStreamSynchronize(e->stream));
+#undef CKE
+    *out = e;
+    return RLB_OK;
+}
+
+void rlb_engine_destroy(rlb_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    void* bufs[] = {e->d_q, e->d_counts, e->d_etr, e->d_vis, e->d_nvis, e->d_rng_n, e->d_eps, e->d_ucb_t, e->d_flag, e->d_env,
+                    e->d_trans, e->d_thr, e->d_thr_state, e->d_totals, e->d_flagword, e->d_episodes, e->d_sums};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (void* b : e->d_stage) if (b) cudaFree(b);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    cudaGetLastError();
+    delete e;
+}
+
+rlb_status rlb_engine_set_stream(rlb_engine* e, void* cuda_stream) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+    e->stream = (cudaStream_t)cuda_stream;
+    return RLB_OK;
+}
+rlb_status rlb_engine_synchronize(rlb_engine* e) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+rlb_status rlb_engine_dims(const rlb_engine* e, uint32_t* n_states, uint32_t* n_actions, uint32_t* n_tables) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    if (n_states) *n_states = e->S;
+    if (n_actions) *n_actions = e->A;
+    if (n_tables) *n_tables = e->T;
+    return RLB_OK;
+}
+uint32_t rlb_engine_store_kind(const rlb_engine* e) { return e ? 1u : 0u; }
+
+// ------------------------------------------------------------------------------- Env
+rlb_status rlb_env_reset(rlb_engine* e, uint32_t* obs_out) {
+    if (!e || !obs_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    StepArgs a;
+    void* dev;
+    CK(stage_out(e, 0, obs_out, N * 4, &dev));
+    a.u32_out = (uint32_t*)dev;
+    CK(dispatch_step(e, OP_ENV_RESET, a));
+    CK(finish_out(e, obs_out, dev, N * 4));
+    return RLB_OK;
+}
+
+rlb_status rlb_env_step(rlb_engine* e, const uint32_t* actions, uint32_t* obs_out, double* reward_out, uint8_t* terminated_out,
+                        uint8_t* not_ready_out) {
+    if (!e || !actions || !obs_out || !reward_out || !terminated_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    StepArgs a;
+    const void* in;
+    void *d_obs, *d_rew, *d_term, *d_nr;
+    CK(stage_in(e, 0, actions, N * 4, &in));
+    a.action = (const uint32_t*)in;
+    CK(stage_out(e, 1, obs_out, N * 4, &d_obs));
+    CK(stage_out(e, 2, reward_out, N * 8, &d_rew));
+    CK(stage_out(e, 3, terminated_out, N, &d_term));
+    CK(stage_out(e, 4, not_ready_out, N, &d_nr));
+    a.u32_out = (uint32_t*)d_obs; a.reward_out = (double*)d_rew; a.term_out = (uint8_t*)d_term; a.not_ready_out = (uint8_t*)d_nr;
+    a.any_not_ready = e->d_flagword;
+    CK(cudaMemsetAsync(e->d_flagword, 0, 4, e->stream));
+    CK(dispatch_step(e, OP_ENV_STEP, a));
+    uint32_t any = 0;
+    CK(cudaMemcpyAsync(&any, e->d_flagword, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(finish_out(e, obs_out, d_obs, N * 4));
+    CK(finish_out(e, reward_out, d_rew, N * 8));
+    CK(finish_out(e, terminated_out, d_term, N));
+    CK(finish_out(e, not_ready_out, d_nr, N));
+    if (any) { set_error("EnvNotReady: step() before reset() or after termination"); return RLB_ERR_ENV_NOT_READY; }
+    return RLB_OK;
+}
+
+// ------------------------------------------------------------------------------- Agent
+rlb_status rlb_agent_get_action(rlb_engine* e, const uint32_t* obs, uint32_t* action_out) {
+    if (!e || !obs || !action_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    StepArgs a;
+    const void* in;
+    void* dev;
+    CK(stage_in(e, 0, obs, N * 4, &in));
+    CK(stage_out(e, 1, action_out, N * 4, &dev));
+    a.obs = (const uint32_t*)in; a.u32_out = (uint32_t*)dev;
+    CK(dispatch_step(e, OP_GET_ACTION, a));
+    CK(finish_out(e, action_out, dev, N * 4));
+    return RLB_OK;
+}
+
+rlb_status rlb_agent_update(rlb_engine* e, const uint32_t* curr_obs, const uint32_t* curr_action, const double* reward,
+                            const uint8_t* terminated, const uint32_t* next_obs, const uint32_t* next_action, void* td_out) {
+    if (!e || !curr_obs || !curr_action || !reward || !terminated || !next_obs || !next_action) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    StepArgs a;
+    const void* in[6];
+    void* dev;
+    CK(stage_in(e, 0, curr_obs, N * 4, &in[0]));
+    CK(stage_in(e, 1, curr_action, N * 4, &in[1]));
+    CK(stage_in(e, 2, reward, N * 8, &in[2]));
+    CK(stage_in(e, 3, terminated, N, &in[3]));
+    CK(stage_in(e, 4, next_obs, N * 4, &in[4]));
+    CK(stage_in(e, 5, next_action, N * 4, &in[5]));
+    CK(stage_out(e, 6, td_out, N * e->real_size, &dev));
+    a.obs = (const uint32_t*)in[0]; a.action = (const uint32_t*)in[1]; a.reward = (const double*)in[2];
+    a.term = (const uint8_t*)in[3]; a.obs2 = (const uint32_t*)in[4]; a.action2 = (const uint32_t*)in[5];
+    a.real_out = dev;
+    CK(dispatch_step(e, OP_UPDATE, a));
+    CK(finish_out(e, td_out, dev, N * e->real_size));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+
+rlb_status rlb_agent_set_future_q_value_func(rlb_engine* e, int32_t target_kind) {
+    if (!e || target_kind < 0 || target_kind > 2) { set_error("bad target_kind"); return RLB_ERR_INVALID_ARG; }
+    e->cfg.target_kind = target_kind;
+    e->dp.target = target_kind;
+    return RLB_OK;
+}
+
+rlb_status rlb_agent_set_action_selector(rlb_engine* e, int32_t selector_kind) {
+    if (!e || selector_kind < 0 || selector_kind > 1) { set_error("bad selector_kind"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    return install_selector(e, selector_kind);
+}
+
+rlb_status rlb_selector_reset(rlb_engine* e) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    if (e->cfg.selector_kind == RLB_SEL_EPS_GREEDY) {
+        CK(fill<double>(e, e->d_eps, N, e->cfg.initial_epsilon));               // uniform_epsilon_greed.rs:78-80
+    } else {
+        CK(cudaMemsetAsync(e->d_counts, 0, e->counts_bytes, e->stream));        // upper_confidence_bound.rs:65-68
+        CK(fill<uint64_t>(e, e->d_ucb_t, N, 1ull));
+    }
+    return RLB_OK;
+}
+
+rlb_status rlb_policy_reset(rlb_engine* e) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    CK(fill_q_default(e));   // tables back to the default row; Double keeps its flag (double_tabular_policy.rs:60-63)
+    return RLB_OK;
+}
+
+rlb_status rlb_agent_reset(rlb_engine* e) {   // one_step_agent.rs:43-46: action_selection.reset(); policy.reset()
+    rlb_status st = rlb_selector_reset(e);
+    if (st != RLB_OK) return st;
+    return rlb_policy_reset(e);
+}
+
+static rlb_status run_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, uint64_t eval_at, rlb_train_out* out,
+                            void* eval_episodes_out, double* eval_sums_out, uint64_t* eval_steps_out) {
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    const size_t rec = episode_rec_size(e);
+    const uint64_t total = end - begin;
+    const bool want_records = mode == 0 ? (out && (out->episodes || out->episode_sums)) : (eval_episodes_out || eval_sums_out);
+    uint64_t chunk = total;
+    if (want_records) {
+        chunk = chunk_episodes(e, total);
+        rlb_status st = ensure_episode_scratch(e, chunk);
+        if (st != RLB_OK) return st;
+    }
+    // trajectory tap
+    rlb_traj_record* d_traj = nullptr;
+    uint64_t* d_traj_count = nullptr;
+    bool own_traj = false, own_count = false;
+    if (mode == 0 && out && out->traj && out->traj_capacity) {
+        if (is_device_ptr(out->traj)) d_traj = out->traj;
+        else { CK(cudaMalloc(&d_traj, N * out->traj_capacity * sizeof(rlb_traj_record))); own_traj = true; }
+        if (out->traj_count && is_device_ptr(out->traj_count)) d_traj_count = out->traj_count;
+        else { CK(cudaMalloc(&d_traj_count, N * sizeof(uint64_t))); own_count = true; }
+        CK(cudaMemsetAsync(d_traj_count, 0, N * sizeof(uint64_t), e->stream));
+    }
+    CK(cudaMemsetAsync(e->d_totals, 0, 4 * sizeof(unsigned long long), e->stream));
+    float ms_total = 0.f;
+    uint32_t launches = 0;
+    for (uint64_t c0 = begin; c0 < end; c0 += chunk) {
+        const uint64_t c1 = std::min<uint64_t>(end, c0 + chunk);
+        DevParams p = e->dp;
+        p.mode = mode;
+        p.eval_at = eval_at;
+        if (mode == 0) { p.ep0 = c0; p.ep1 = c1; p.n_eval = 0; }
+        else { p.ep0 = p.ep1 = 0; p.n_eval = c1 - c0; }
+        p.episodes = want_records ? e->d_episodes : nullptr;
+        p.traj = d_traj; p.traj_cap = d_traj ? out->traj_capacity : 0; p.traj_count = d_traj_count;
+        CK(cudaEventRecord(e->ev0, e->stream));
+        CK(dispatch_run(e, p));
+        CK(cudaEventRecord(e->ev1, e->stream));
+        launches += 1;
+        const uint64_t n_ep = c1 - c0;
+        double* sums_dst = mode == 0 ? (out ? out->episode_sums : nullptr) : eval_sums_out;
+        void* rec_dst = mode == 0 ? (out ? out->episodes : nullptr) : eval_episodes_out;
+        if (sums_dst) {
+            rlb_status st = reduce_episodes(e, n_ep);
+            if (st != RLB_OK) return st;
+            CK(copy_out(e, sums_dst + (c0 - begin) * 4, e->d_sums, n_ep * 4 * sizeof(double)));
+        }
+        if (rec_dst) CK(copy_out(e, (char*)rec_dst + (c0 - begin) * N * rec, e->d_episodes, n_ep * N * rec));
+        CK(cudaEventSynchronize(e->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        ms_total += ms;
+    }
+    unsigned long long totals[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(totals, e->d_totals, sizeof totals, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (d_traj) {
+        if (own_traj) { CK(copy_out(e, out->traj, d_traj, N * out->traj_capacity * sizeof(rlb_traj_record))); cudaFree(d_traj); }
+        if (own_count) { if (out->traj_count) CK(copy_out(e, out->traj_count, d_traj_count, N * sizeof(uint64_t))); cudaFree(d_traj_count); }
+    }
+    double eval_ret;
+    std::memcpy(&eval_ret, &totals[3], 8);
+    if (mode == 0 && out) {
+        out->train_steps = totals[0]; out->eval_steps = totals[1]; out->eval_episodes = totals[2];
+        out->eval_return_sum = eval_ret; out->kernel_ms = ms_total; out->kernel_launches = launches;
+    }
+    if (mode == 1 && eval_steps_out) *eval_steps_out = totals[1];
+    return RLB_OK;
+}
+
+rlb_status rlb_agent_train_range(rlb_engine* e, uint64_t ep_begin, uint64_t ep_end, uint64_t eval_at, rlb_train_out* out) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    if (eval_at == 0) { set_error("eval_at == 0 (the reference divides by it, agent.rs:107)"); return RLB_ERR_INVALID_ARG; }
+    if (ep_end < ep_begin) { set_error("ep_end < ep_begin"); return RLB_ERR_INVALID_ARG; }
+    return run_range(e, 0, ep_begin, ep_end, eval_at, out, nullptr, nullptr, nullptr);
+}
+rlb_status rlb_agent_train(rlb_engine* e, uint64_t n_episodes, uint64_t eval_at, rlb_train_out* out) {
+    return rlb_agent_train_range(e, 0, n_episodes, eval_at, out);
+}
+rlb_status rlb_agent_evaluate(rlb_engine* e, uint64_t n_episodes, void* episodes_out, double* sums_out, uint64_t* total_steps_out) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    return run_range(e, 1, 0, n_episodes, 1, nullptr, episodes_out, sums_out, total_steps_out);
+}
+
+// ------------------------------------------------------------------------------- Policy
+static rlb_status policy_rows(rlb_engine* e, const uint32_t* obs, void* values_out, int which) {
+    if (!e || !obs || !values_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    StepArgs a;
+    const void* in;
+    void* dev;
+    CK(stage_in(e, 0, obs, N * 4, &in));
+    CK(stage_out(e, 1, values_out, N * e->A * e->real_size, &dev));
+    a.obs = (const uint32_t*)in; a.real_out = dev; a.which = which;
+    CK(dispatch_step(e, OP_POLICY_ROWS, a));
+    CK(finish_out(e, values_out, dev, N * e->A * e->real_size));
+    return RLB_OK;
+}
+rlb_status rlb_policy_predict(rlb_engine* e, const uint32_t* obs, void* values_out) { return policy_rows(e, obs, values_out, 0); }
+rlb_status rlb_policy_get_values(rlb_engine* e, const uint32_t* obs, void* values_out) { return policy_rows(e, obs, values_out, 1); }
+
+rlb_status rlb_policy_update(rlb_engine* e, const uint32_t* obs, const uint32_t* action, const uint32_t* next_obs, const void* temporal_difference) {
+    (void)next_obs;   // unused by both tabular policies (tabular_policy.rs:35 `_next_obs`)
+    if (!e || !obs || !action || !temporal_difference) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    StepArgs a;
+    const void* in[3];
+    CK(stage_in(e, 0, obs, N * 4, &in[0]));
+    CK(stage_in(e, 1, action, N * 4, &in[1]));
+    CK(stage_in(e, 2, temporal_difference, N * e->real_size, &in[2]));
+    a.obs = (const uint32_t*)in[0]; a.action = (const uint32_t*)in[1]; a.td_in = in[2];
+    CK(dispatch_step(e, OP_POLICY_UPDATE, a));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+rlb_status rlb_policy_after_update(rlb_engine* e) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->cfg.policy_kind == RLB_POLICY_DOUBLE) {
+        const uint64_t N = e->cfg.n_agents;
+        k_flag_flip<<<(unsigned)((N + 255) / 256), 256, 0, e->stream>>>(e->d_flag, N);
+        CK(cudaGetLastError());
+    }
+    return RLB_OK;
+}
+
+// ------------------------------------------------------------------------------- ActionSelection
+rlb_status rlb_selector_get_action(rlb_engine* e, const uint32_t* obs, const void* values, uint32_t* action_out) {
+    if (!e || !obs || !values || !action_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    StepArgs a;
+    const void* in[2];
+    void* dev;
+    CK(stage_in(e, 0, obs, N * 4, &in[0]));
+    CK(stage_in(e, 1, values, N * e->A * e->real_size, &in[1]));
+    CK(stage_out(e, 2, action_out, N * 4, &dev));
+    a.obs = (const uint32_t*)in[0]; a.values = in[1]; a.u32_out = (uint32_t*)dev;
+    CK(dispatch_step(e, OP_SELECTOR_GET_ACTION, a));
+    CK(finish_out(e, action_out, dev, N * 4));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+rlb_status rlb_selector_get_exploration_probs(rlb_engine* e, const uint32_t* obs, const void* values, void* probs_out) {
+    if (!e || !obs || !values || !probs_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    StepArgs a;
+    const void* in[2];
+    void* dev;
+    CK(stage_in(e, 0, obs, N * 4, &in[0]));
+    CK(stage_in(e, 1, values, N * e->A * e->real_size, &in[1]));
+    CK(stage_out(e, 2, probs_out, N * e->A * e->real_size, &dev));
+    a.obs = (const uint32_t*)in[0]; a.values = in[1]; a.real_out = dev;
+    CK(dispatch_step(e, OP_SELECTOR_PROBS, a));
+    CK(finish_out(e, probs_out, dev, N * e->A * e->real_size));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+rlb_status rlb_selector_update(rlb_engine* e) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->cfg.selector_kind == RLB_SEL_EPS_GREEDY) {
+        const uint64_t N = e->cfg.n_agents;
+        k_eps_decay<<<(unsigned)((N + 255) / 256), 256, 0, e->stream>>>(e->d_eps, N, e->cfg.decay_kind, e->cfg.epsilon_decay, e->cfg.final_epsilon);
+        CK(cudaGetLastError());
+    }
+    return RLB_OK;
+}
+
+// ------------------------------------------------------------------------------- snapshots
+rlb_status rlb_download_tables(rlb_engine* e, void* q_out, uint32_t* counts_out) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    if (q_out) {
+        const size_t n_el = (size_t)N * e->T * e->S * e->A;
+        void* dev;
+        CK(stage_out(e, 7, q_out, n_el * e->real_size, &dev));
+        unsigned grid = (unsigned)std::min<uint64_t>((n_el + 255) / 256, 148u * 32u);
+        if (e->cfg.real_kind == RLB_REAL_F32) k_pack_q<float><<<grid, 256, 0, e->stream>>>((const float*)e->d_q, (float*)dev, N, e->S, e->T, e->A, e->APAD);
+        else k_pack_q<double><<<grid, 256, 0, e->stream>>>((const double*)e->d_q, (double*)dev, N, e->S, e->T, e->A, e->APAD);
+        CK(cudaGetLastError());
+        CK(finish_out(e, q_out, dev, n_el * e->real_size));
+    }
+    if (counts_out) {
+        const size_t n_el = (size_t)N * e->S * e->A;
+        void* dev;
+        CK(stage_out(e, 7, counts_out, n_el * 4, &dev));
+        if (e->d_counts) {
+            unsigned grid = (unsigned)std::min<uint64_t>((n_el + 255) / 256, 148u * 32u);
+            k_pack_q<uint32_t><<<grid, 256, 0, e->stream>>>(e->d_counts, (uint32_t*)dev, N, e->S, 1, e->A, e->APAD);
+            CK(cudaGetLastError());
+        } else {
+            CK(cudaMemsetAsync(dev, 0, n_el * 4, e->stream));
+        }
+        CK(finish_out(e, counts_out, dev, n_el * 4));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+
+rlb_status rlb_upload_tables(rlb_engine* e, const void* q, const uint32_t* counts) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    if (q) {
+        const size_t n_el = (size_t)N * e->T * e->S * e->A;
+        const void* dev;
+        CK(stage_in(e, 7, q, n_el * e->real_size, &dev));
+        unsigned grid = (unsigned)std::min<uint64_t>((n_el + 255) / 256, 148u * 32u);
+        if (e->cfg.real_kind == RLB_REAL_F32) k_unpack_q<float><<<grid, 256, 0, e->stream>>>((float*)e->d_q, (const float*)dev, N, e->S, e->T, e->A, e->APAD);
+        else k_unpack_q<double><<<grid, 256, 0, e->stream>>>((double*)e->d_q, (const double*)dev, N, e->S, e->T, e->A, e->APAD);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    if (counts) {
+        if (!e->d_counts) { set_error("engine has no UCB counts (selector is eps-greedy)"); return RLB_ERR_INVALID_ARG; }
+        const size_t n_el = (size_t)N * e->S * e->A;
+        const void* dev;
+        CK(stage_in(e, 7, counts, n_el * 4, &dev));
+        unsigned grid = (unsigned)std::min<uint64_t>((n_el + 255) / 256, 148u * 32u);
+        k_unpack_q<uint32_t><<<grid, 256, 0, e->stream>>>(e->d_counts, (const uint32_t*)dev, N, e->S, 1, e->A, e->APAD);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return RLB_OK;
+}
+
+rlb_status rlb_get_agent_states(rlb_engine* e, rlb_agent_state* states_out) {
+    if (!e || !states_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    if (is_device_ptr(states_out)) { set_error("states_out must be a host pointer"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    std::vector<double> eps(N);
+    std::vector<uint64_t> t(N), n(N);
+    std::vector<uint8_t> flag(N);
+    std::vector<EnvState> env(N);
+    CK(cudaMemcpyAsync(eps.data(), e->d_eps, N * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(t.data(), e->d_ucb_t, N * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(n.data(), e->d_rng_n, N * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(flag.data(), e->d_flag, N, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(env.data(), e->d_env, N * sizeof(EnvState), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (uint64_t i = 0; i < N; ++i) states_out[i] = rlb_agent_state{eps[i], t[i], n[i], flag[i] ? 1 : 0, env[i].ready ? 1 : 0};
+    return RLB_OK;
+}
+
+rlb_status rlb_set_agent_states(rlb_engine* e, const rlb_agent_state* states) {
+    if (!e || !states) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    if (is_device_ptr(states)) { set_error("states must be a host pointer"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    std::vector<double> eps(N);
+    std::vector<uint64_t> t(N), n(N);
+    std::vector<uint8_t> flag(N);
+    for (uint64_t i = 0; i < N; ++i) { eps[i] = states[i].epsilon; t[i] = states[i].ucb_t; n[i] = states[i].rng_n; flag[i] = states[i].policy_flag ? 1 : 0; }
+    CK(cudaMemcpyAsync(e->d_eps, eps.data(), N * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_ucb_t, t.data(), N * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_rng_n, n.data(), N * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_flag, flag.data(), N, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+
+// ------------------------------------------------------------------------------- host RNG contract
+void rlb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { host_philox(ctr, key, out); }
+void rlb_rng_words(uint64_t seed, uint64_t agent_id, uint64_t first_word, uint64_t count, uint32_t* out) {
+    for (uint64_t i = 0; i < count; ++i) out[i] = host_word(seed, agent_id, first_word + i);
+}
+static uint64_t host_u64(uint64_t seed, uint64_t agent, uint64_t* n) {
+    uint64_t lo = host_word(seed, agent, (*n)++);
+    uint64_t hi = host_word(seed, agent, (*n)++);
+    return lo | (hi << 32);
+}
+double rlb_rng_uniform_f64(uint64_t seed, uint64_t agent_id, uint64_t* word_index) {
+    return (double)(host_u64(seed, agent_id, word_index) >> 12) * 0x1p-52;
+}
+uint64_t rlb_rng_uniform_usize(uint64_t seed, uint64_t agent_id, uint64_t* word_index, uint64_t range) {
+    if (range == 0) return host_u64(seed, agent_id, word_index);
+    const uint64_t zone = UINT64_MAX - (UINT64_MAX - range + 1) % range;
+    for (;;) {
+        const uint64_t v = host_u64(seed, agent_id, word_index);
+        const unsigned __int128 m = (unsigned __int128)v * range;
+        if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
+    }
+}
+uint32_t rlb_rng_card(uint64_t seed, uint64_t agent_id, uint64_t* word_index) {
+    for (;;) {
+        const uint64_t m = (uint64_t)host_word(seed, agent_id, (*word_index)++) * 10u;
+        if ((uint32_t)m <= 0xfffffff9u) return 1u + (uint32_t)(m >> 32);
+    }
+}
+
+// ------------------------------------------------------------------------------- Blackjack ids
+void rlb_blackjack_decode(uint32_t dense_index, uint32_t* p_score, uint32_t* d_score, uint32_t* p_ace) {
+    if (p_ace) *p_ace = dense_index & 1u;
+    if (d_score) *d_score = (dense_index >> 1) % 26u + 1u;
+    if (p_score) *p_score = (dense_index >> 1) / 26u + 4u;
+}
+uint64_t rlb_blackjack_obs_id(uint32_t dense_index) {
+    uint32_t p, d, a;
+    rlb_blackjack_decode(dense_index, &p, &d, &a);
+    return blackjack_id(p, d, a);
+}
+uint32_t rlb_blackjack_dense_index(uint64_t obs_id) {
+    for (uint32_t i = 0; i < 1456; ++i) if (rlb_blackjack_obs_id(i) == obs_id) return i;
+    return 0xffffffffu;
+}
+
+}   // extern "C"

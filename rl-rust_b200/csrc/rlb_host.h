@@ -1,0 +1,24 @@
+// rlb_host.h — host-only helpers of librlb (see rlb_host.cpp).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/rlb.h"
+
+namespace rlb {
+
+struct EnvTables {
+    uint32_t S = 0, A = 0;
+    std::vector<uint16_t> trans;       // s' | rcode << 10 | terminated << 15
+    std::vector<uint64_t> thr;         // Taxi start thresholds (k-space)
+    std::vector<uint16_t> thr_state;
+    uint64_t slip_thr0 = 0, slip_thr1 = 0;
+};
+
+bool build_env_tables(const rlb_config& cfg, EnvTables& out, std::string& err);
+void host_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+uint32_t host_word(uint64_t seed, uint64_t agent, uint64_t n);
+uint64_t blackjack_id(uint32_t p, uint32_t d, uint32_t ace);
+
+}   // namespace rlb

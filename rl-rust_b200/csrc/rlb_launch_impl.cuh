@@ -1,0 +1,106 @@
+// rlb_launch_impl.cuh — definitions behind rlb_launch.h; included by rlb_inst_<env>.cu only.
+#pragma once
+#include "rlb_launch.h"
+#include "rlb_step_kernels.cuh"
+
+namespace rlb {
+
+#define RLB_VARIANT_SWITCH(v, CALL)                                                    \
+    switch (((v).real << 3) | ((v).policy << 2) | ((v).sel << 1) | (v).trace) {        \
+        case 0: CALL(float, 0, 0, false); break;                                       \
+        case 1: CALL(float, 0, 0, true); break;                                        \
+        case 2: CALL(float, 0, 1, false); break;                                       \
+        case 3: CALL(float, 0, 1, true); break;                                        \
+        case 4: CALL(float, 1, 0, false); break;                                       \
+        case 5: CALL(float, 1, 0, true); break;                                        \
+        case 6: CALL(float, 1, 1, false); break;                                       \
+        case 7: CALL(float, 1, 1, true); break;                                        \
+        case 8: CALL(double, 0, 0, false); break;                                      \
+        case 9: CALL(double, 0, 0, true); break;                                       \
+        case 10: CALL(double, 0, 1, false); break;                                     \
+        case 11: CALL(double, 0, 1, true); break;                                      \
+        case 12: CALL(double, 1, 0, false); break;                                     \
+        case 13: CALL(double, 1, 0, true); break;                                      \
+        case 14: CALL(double, 1, 1, false); break;                                     \
+        case 15: CALL(double, 1, 1, true); break;                                      \
+        default: return cudaErrorInvalidValue;                                         \
+    }
+
+constexpr int kBlock = 128;
+static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+template <int ENV>
+cudaError_t launch_run(const Variant& v, const DevParams& p, cudaStream_t stream) {
+    const unsigned grid = grid_for(p.n_agents);
+    const size_t smem = EnvTab<ENV>::smem_bytes(p.S);
+#define RLB_CALL(R, P, S, T) k_run<ENV, R, P, S, T><<<grid, kBlock, smem, stream>>>(p)
+    RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+    return cudaGetLastError();
+}
+
+template <int ENV>
+cudaError_t run_kernel_attributes(const Variant& v, cudaFuncAttributes* attr) {
+#define RLB_CALL(R, P, S, T) return cudaFuncGetAttributes(attr, k_run<ENV, R, P, S, T>)
+    RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+    return cudaSuccess;
+}
+
+template <int ENV>
+cudaError_t launch_step(StepOp op, const Variant& v, const DevParams& p, const StepArgs& a, cudaStream_t stream) {
+    const unsigned grid = grid_for(p.n_agents);
+    const size_t smem = EnvTab<ENV>::smem_bytes(p.S);
+    switch (op) {
+        case OP_ENV_CONSTRUCT: k_env_construct<ENV><<<grid, kBlock, 0, stream>>>(p); break;
+        case OP_ENV_RESET: k_env_reset<ENV><<<grid, kBlock, smem, stream>>>(p, a.u32_out); break;
+        case OP_ENV_STEP:
+            k_env_step<ENV><<<grid, kBlock, smem, stream>>>(p, a.action, a.u32_out, a.reward_out, a.term_out, a.not_ready_out, a.any_not_ready);
+            break;
+        case OP_GET_ACTION: {
+#define RLB_CALL(R, P, S, T) k_get_action<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.u32_out)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            break;
+        }
+        case OP_UPDATE: {
+#define RLB_CALL(R, P, S, T) \
+    k_update<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.action, a.reward, a.term, a.obs2, a.action2, (R*)a.real_out)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            break;
+        }
+        case OP_POLICY_ROWS: {
+#define RLB_CALL(R, P, S, T) k_policy_rows<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (R*)a.real_out, a.which)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            break;
+        }
+        case OP_POLICY_UPDATE: {
+#define RLB_CALL(R, P, S, T) k_policy_update<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.action, (const R*)a.td_in)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            break;
+        }
+        case OP_SELECTOR_GET_ACTION: {
+#define RLB_CALL(R, P, S, T) k_selector_get_action<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (const R*)a.values, a.u32_out)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            break;
+        }
+        case OP_SELECTOR_PROBS: {
+#define RLB_CALL(R, P, S, T) k_selector_probs<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (const R*)a.values, (R*)a.real_out)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            break;
+        }
+    }
+    return cudaGetLastError();
+}
+
+#define RLB_INSTANTIATE_ENV(ENV)                                                                         \
+    template cudaError_t launch_run<ENV>(const Variant&, const DevParams&, cudaStream_t);                \
+    template cudaError_t launch_step<ENV>(StepOp, const Variant&, const DevParams&, const StepArgs&, cudaStream_t); \
+    template cudaError_t run_kernel_attributes<ENV>(const Variant&, cudaFuncAttributes*);
+
+}   // namespace rlb

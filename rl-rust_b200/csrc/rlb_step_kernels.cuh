@@ -1,0 +1,254 @@
+// rlb_step_kernels.cuh — the individual trait methods of the reference, batched over the
+// engine's agents (one thread per agent).  They share AgentCore / EnvRegs with the fused
+// kernel, so a host loop over these calls reproduces k_run bit for bit; they exist for the
+// drop-in trait objects (N = 1 or a few) and for step-level parity tests.
+#pragma once
+#include "rlb_device.cuh"
+
+namespace rlb {
+
+// Env::new() — only Blackjack's constructor touches the RNG (deals a hand, blackjack.rs:57).
+template <int ENV>
+__global__ void k_env_construct(const DevParams p) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    EnvState es;
+    es.pos = 0; es.curr_step = 0; es.ready = 0;
+    es.p_sum = es.d_sum = es.d_first = 0; es.p_ace = es.d_ace = 0; es.pad[0] = es.pad[1] = 0;
+    if constexpr (ENV == RLB_ENV_BLACKJACK) {
+        Rng rng;
+        rng.init(p.seed, p.first_agent + i, p.rng_n[i]);
+        EnvRegs<RLB_ENV_BLACKJACK> env;
+        env.deal(rng);
+        env.to_state(es, 0);
+        p.rng_n[i] = rng.n;
+    }
+    p.env[i] = es;
+}
+
+// Env::reset
+template <int ENV>
+__global__ void __launch_bounds__(128) k_env_reset(const DevParams p, uint32_t* obs_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EnvTab<ENV> tab;
+    tab.load(p, smem_raw);
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    Rng rng;
+    rng.init(p.seed, p.first_agent + i, p.rng_n[i]);
+    EnvState es = p.env[i];
+    EnvRegs<ENV> env;
+    env.from_state(es);
+    uint32_t o = env.reset(rng, tab, p);
+    env.to_state(es, o);
+    es.pos = o;
+    es.ready = 1;
+    p.env[i] = es;
+    p.rng_n[i] = rng.n;
+    obs_out[i] = o;
+}
+
+// Env::step.  Err(EnvNotReady) -> agent untouched, not_ready flag set.
+template <int ENV>
+__global__ void __launch_bounds__(128) k_env_step(const DevParams p, const uint32_t* actions, uint32_t* obs_out,
+                                                   double* reward_out, uint8_t* term_out, uint8_t* not_ready_out,
+                                                   uint32_t* any_not_ready) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EnvTab<ENV> tab;
+    tab.load(p, smem_raw);
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    EnvState es = p.env[i];
+    if (!es.ready) {
+        if (not_ready_out) not_ready_out[i] = 1;
+        atomicOr(any_not_ready, 1u);
+        return;
+    }
+    if (not_ready_out) not_ready_out[i] = 0;
+    Rng rng;
+    rng.init(p.seed, p.first_agent + i, p.rng_n[i]);
+    EnvRegs<ENV> env;
+    env.from_state(es);
+    uint32_t o;
+    double r;
+    bool term;
+    env.template step<double>(es.pos, actions[i], rng, tab, p, o, r, term);
+    // a truncated step reports obs 0 but does not move the env (taxi.rs:148-151)
+    const bool truncated = (ENV != RLB_ENV_BLACKJACK) && es.curr_step >= p.max_steps;
+    env.to_state(es, truncated ? es.pos : o);
+    if (term) es.ready = 0;
+    p.env[i] = es;
+    p.rng_n[i] = rng.n;
+    obs_out[i] = o;
+    reward_out[i] = r;
+    term_out[i] = term ? 1 : 0;
+}
+
+// Agent::get_action = selector.get_action(obs, policy.predict(obs))
+template <int ENV, typename Real, int POLICY, int SEL, bool TRACE>
+__global__ void __launch_bounds__(128) k_get_action(const DevParams p, const uint32_t* obs, uint32_t* action_out) {
+    using Core = AgentCore<ENV, Real, POLICY, SEL, TRACE>;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    Core core;
+    core.load(p, i);
+    Real pred[Core::A], vals[Core::A];
+    core.rows(obs[i], pred, vals);
+    action_out[i] = core.select(obs[i], pred, p);
+    core.save(p, i);
+}
+
+// Agent::update
+template <int ENV, typename Real, int POLICY, int SEL, bool TRACE>
+__global__ void __launch_bounds__(128) k_update(const DevParams p, const uint32_t* s, const uint32_t* a, const double* reward,
+                                                 const uint8_t* term, const uint32_t* s2, const uint32_t* a2, Real* td_out) {
+    using Core = AgentCore<ENV, Real, POLICY, SEL, TRACE>;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    Core core;
+    core.load(p, i);
+    Real pred[Core::A], vals[Core::A];
+    core.rows(s2[i], pred, vals);
+    Real td = core.update(s[i], a[i], (Real)reward[i], term[i] != 0, s2[i], a2[i], vals, p);
+    if (td_out) td_out[i] = td;
+    core.save(p, i);
+}
+
+// Policy::predict (which = 0) / Policy::get_values (which = 1)
+template <int ENV, typename Real, int POLICY, int SEL, bool TRACE>
+__global__ void __launch_bounds__(128) k_policy_rows(const DevParams p, const uint32_t* obs, Real* out, int which) {
+    using Core = AgentCore<ENV, Real, POLICY, SEL, TRACE>;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    Core core;
+    core.load(p, i);
+    Real pred[Core::A], vals[Core::A];
+    core.rows(obs[i], pred, vals);
+#pragma unroll
+    for (int k = 0; k < Core::A; ++k) out[i * Core::A + k] = which == 0 ? pred[k] : vals[k];
+}
+
+// Policy::update: (Basic: Q | Double: beta if flag else alpha)[obs][action] += lr * td
+template <int ENV, typename Real, int POLICY, int SEL, bool TRACE>
+__global__ void __launch_bounds__(128) k_policy_update(const DevParams p, const uint32_t* obs, const uint32_t* action, const Real* td) {
+    using Core = AgentCore<ENV, Real, POLICY, SEL, TRACE>;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    Core core;
+    core.load(p, i);
+    const int write_tbl = (POLICY == RLB_POLICY_DOUBLE && core.flag) ? 1 : 0;
+    Real old = core.st.get_q(obs[i], write_tbl, action[i]);
+    core.st.set_q(obs[i], write_tbl, action[i], old + core.lr * td[i]);
+}
+
+// ActionSelection::get_action on caller-supplied values
+template <int ENV, typename Real, int POLICY, int SEL, bool TRACE>
+__global__ void __launch_bounds__(128) k_selector_get_action(const DevParams p, const uint32_t* obs, const Real* values, uint32_t* action_out) {
+    using Core = AgentCore<ENV, Real, POLICY, SEL, TRACE>;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    Core core;
+    core.load(p, i);
+    Real v[Core::A];
+#pragma unroll
+    for (int k = 0; k < Core::A; ++k) v[k] = values[i * Core::A + k];
+    action_out[i] = core.select(obs[i], v, p);
+    core.save(p, i);
+}
+
+// ActionSelection::get_exploration_probs on caller-supplied values
+template <int ENV, typename Real, int POLICY, int SEL, bool TRACE>
+__global__ void __launch_bounds__(128) k_selector_probs(const DevParams p, const uint32_t* obs, const Real* values, Real* probs_out) {
+    using Core = AgentCore<ENV, Real, POLICY, SEL, TRACE>;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    Core core;
+    core.load(p, i);
+    Real v[Core::A], pr[Core::A];
+#pragma unroll
+    for (int k = 0; k < Core::A; ++k) v[k] = values[i * Core::A + k];
+    core.probs(obs[i], v, pr, p);
+#pragma unroll
+    for (int k = 0; k < Core::A; ++k) probs_out[i * Core::A + k] = pr[k];
+}
+
+// ActionSelection::update for eps-greedy: decay_epsilon (uniform_epsilon_greed.rs:42-49)
+static __global__ void k_eps_decay(double* eps, uint64_t n, int kind, double param, double final_eps) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) eps[i] = decay_epsilon(eps[i], kind, param, final_eps);
+}
+// Policy::after_update for Double
+static __global__ void k_flag_flip(uint8_t* flag, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = flag[i] ? 0 : 1;
+}
+
+template <typename V>
+__global__ void k_fill(V* ptr, uint64_t n, V value) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) ptr[i] = value;
+}
+
+// padded device layout [N][S][T][APAD] <-> ABI layout [N][T][S][A]
+template <typename V>
+__global__ void k_pack_q(const V* padded, V* packed, uint64_t n_agents, uint32_t S, uint32_t T, uint32_t A, uint32_t APAD) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = n_agents * S * T * A;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; idx < total; idx += stride) {
+        uint32_t a = idx % A;
+        uint64_t r = idx / A;
+        uint32_t s = r % S; r /= S;
+        uint32_t t = r % T;
+        uint64_t n = r / T;
+        packed[idx] = padded[((n * S + s) * T + t) * APAD + a];
+    }
+}
+template <typename V>
+__global__ void k_unpack_q(V* padded, const V* packed, uint64_t n_agents, uint32_t S, uint32_t T, uint32_t A, uint32_t APAD) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = n_agents * S * T * A;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; idx < total; idx += stride) {
+        uint32_t a = idx % A;
+        uint64_t r = idx / A;
+        uint32_t s = r % S; r /= S;
+        uint32_t t = r % T;
+        uint64_t n = r / T;
+        padded[((n * S + s) * T + t) * APAD + a] = packed[idx];
+    }
+}
+
+// Per-episode-index reduction over this engine's agents of the streamed episode records:
+// out[e] = (sum length, sum return, sum td_sum, sum td_abs_sum) in f64, fixed tree order.
+// One CTA per episode index; coalesced 16/32-byte record reads.
+template <typename Real>
+__global__ void __launch_bounds__(256) k_episode_sums(const void* episodes, uint64_t n_agents, double* out) {
+    using Rec = typename EpisodeRec<Real>::type;
+    const Rec* rec = reinterpret_cast<const Rec*>(episodes) + (uint64_t)blockIdx.x * n_agents;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (uint64_t i = threadIdx.x; i < n_agents; i += blockDim.x) {
+        Rec r = rec[i];
+        acc[0] += (double)r.length;
+        acc[1] += (double)r.ret;
+        acc[2] += (double)r.td_sum;
+        acc[3] += (double)r.td_abs_sum;
+    }
+    __shared__ double sm[4][256];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sm[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) out[(uint64_t)blockIdx.x * 4 + threadIdx.x] = sm[threadIdx.x][0];
+}
+
+}   // namespace rlb
