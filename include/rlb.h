@@ -162,6 +162,7 @@ typedef struct rlb_train_out {
     uint64_t eval_episodes;      /* out */
     float kernel_ms;             /* out: device time of the fused kernel launches (CUDA events) */
     uint32_t kernel_launches;    /* out */
+    uint64_t trace_rows;         /* out: eligibility rows swept (elegibility_traces_agent.rs:86), for the roofline */
 } rlb_train_out;
 
 /* Complete per-agent resumable state besides the tables. */

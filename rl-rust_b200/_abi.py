@@ -42,7 +42,7 @@ class RlbTrainOut(C.Structure):
         ("episode_sums", C.c_void_p), ("episodes", C.c_void_p), ("traj", C.c_void_p), ("traj_capacity", C.c_uint64),
         ("traj_count", C.c_void_p), ("train_steps", C.c_uint64), ("eval_steps", C.c_uint64),
         ("eval_return_sum", C.c_double), ("eval_episodes", C.c_uint64), ("kernel_ms", C.c_float),
-        ("kernel_launches", C.c_uint32),
+        ("kernel_launches", C.c_uint32), ("trace_rows", C.c_uint64),
     ]
 
 
@@ -235,7 +235,8 @@ class Engine:
             out.traj_count = ptr(res["traj_count"])
         check(lib.rlb_agent_train_range(self.h, ep_begin, n_episodes, eval_at, C.byref(out)))
         res.update(train_steps=out.train_steps, eval_steps=out.eval_steps, eval_return_sum=out.eval_return_sum,
-                   eval_episodes=out.eval_episodes, kernel_ms=out.kernel_ms, kernel_launches=out.kernel_launches)
+                   eval_episodes=out.eval_episodes, kernel_ms=out.kernel_ms, kernel_launches=out.kernel_launches,
+                   trace_rows=out.trace_rows)
         return res
 
     def evaluate(self, n_episodes, *, sums=True, episodes=False):

@@ -68,7 +68,7 @@ struct rlb_engine {
     uint16_t* d_trans = nullptr;
     uint64_t* d_thr = nullptr;
     uint16_t* d_thr_state = nullptr;
-    unsigned long long* d_totals = nullptr;   // [4]: train steps, eval steps, eval episodes, (double) eval return
+    unsigned long long* d_totals = nullptr;   // [8]: train steps, eval steps, eval episodes, (double) eval return, trace rows
     uint32_t* d_flagword = nullptr;
     // scratch
     void* d_episodes = nullptr; size_t episodes_cap = 0;
@@ -294,7 +294,7 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     CKE(cudaMalloc(&e->d_ucb_t, N * sizeof(uint64_t)));
     CKE(cudaMalloc(&e->d_flag, N * sizeof(uint8_t)));
     CKE(cudaMalloc(&e->d_env, N * sizeof(EnvState)));
-    CKE(cudaMalloc(&e->d_totals, 4 * sizeof(unsigned long long)));
+    CKE(cudaMalloc(&e->d_totals, 8 * sizeof(unsigned long long)));
     CKE(cudaMalloc(&e->d_flagword, sizeof(uint32_t)));
     if (!e->tables.trans.empty()) {
         CKE(cudaMalloc(&e->d_trans, e->tables.trans.size() * sizeof(uint16_t)));
@@ -519,7 +519,7 @@ static rlb_status run_range(rlb_engine* e, int mode, uint64_t begin, uint64_t en
         else { CK(cudaMalloc(&d_traj_count, N * sizeof(uint64_t))); own_count = true; }
         CK(cudaMemsetAsync(d_traj_count, 0, N * sizeof(uint64_t), e->stream));
     }
-    CK(cudaMemsetAsync(e->d_totals, 0, 4 * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->d_totals, 0, 8 * sizeof(unsigned long long), e->stream));
     float ms_total = 0.f;
     uint32_t launches = 0;
     for (uint64_t c0 = begin; c0 < end; c0 += chunk) {
@@ -549,7 +549,7 @@ static rlb_status run_range(rlb_engine* e, int mode, uint64_t begin, uint64_t en
         CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
         ms_total += ms;
     }
-    unsigned long long totals[4] = {0, 0, 0, 0};
+    unsigned long long totals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(totals, e->d_totals, sizeof totals, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (d_traj) {
@@ -560,7 +560,7 @@ static rlb_status run_range(rlb_engine* e, int mode, uint64_t begin, uint64_t en
     std::memcpy(&eval_ret, &totals[3], 8);
     if (mode == 0 && out) {
         out->train_steps = totals[0]; out->eval_steps = totals[1]; out->eval_episodes = totals[2];
-        out->eval_return_sum = eval_ret; out->kernel_ms = ms_total; out->kernel_launches = launches;
+        out->eval_return_sum = eval_ret; out->kernel_ms = ms_total; out->kernel_launches = launches; out->trace_rows = totals[4];
     }
     if (mode == 1 && eval_steps_out) *eval_steps_out = totals[1];
     return RLB_OK;
