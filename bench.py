@@ -226,6 +226,7 @@ def main():
     import torch.distributed as dist
     import parity as P
     rlb = importlib.import_module("rl-rust_b200")
+    sh = importlib.import_module("rl-rust_b200.sharding")
     if not torch.cuda.is_available() or rlb.abi.lib.rlb_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
 
@@ -240,14 +241,13 @@ def main():
     eval_at = max(1, n_ep // 10)
     chunks_per_run = n_ep // chunk
     h = workload_hyper(w)
-    eng = P.make_engine(combo(w, real), h, N, first_agent_id=rank * N, device=local_rank)
+    eng = P.make_engine(combo(w, real), h, N, first_agent_id=sh.shard(rank, N), device=local_rank)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     apad = 8 if eng.A == 6 else eng.A
     table_bytes = N * eng.S * eng.T * apad * real_size
 
     sums_dev = torch.zeros((chunk, 4), dtype=torch.float64, device="cuda")
-    gather_list = [torch.zeros_like(sums_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
     rec_dtype_size = 16 if real == 0 else 32
     state = {"k": 0}
     acc = {"train_steps": 0, "eval_steps": 0, "kernel_ms": 0.0, "launches": 0, "trace_rows": 0}
@@ -264,7 +264,7 @@ def main():
         if world > 1:                                           # the run's one collective: per-episode metrics to rank 0
             if host_out is not None:
                 sums_dev.copy_(host_out[0], non_blocking=True)
-            dist.gather(sums_dev, gather_list, dst=0)
+            state["curves"] = sh.gather_episode_sums(sums_dev)   # [world, chunk, 4] on rank 0
         state["k"] = k + 1
         if count:
             acc["train_steps"] += r["train_steps"]; acc["eval_steps"] += r["eval_steps"]
