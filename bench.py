@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--real", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--store", type=int, default=0, help="table store: 0 auto, 1 HBM, 2 shared memory")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.agents_per_gpu:
@@ -241,7 +242,7 @@ def main():
     eval_at = max(1, n_ep // 10)
     chunks_per_run = n_ep // chunk
     h = workload_hyper(w)
-    eng = P.make_engine(combo(w, real), h, N, first_agent_id=sh.shard(rank, N), device=local_rank)
+    eng = P.make_engine(combo(w, real), h, N, first_agent_id=sh.shard(rank, N), device=local_rank, store_kind=args.store)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     apad = 8 if eng.A == 6 else eng.A
@@ -336,6 +337,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": args.real, "data": "synthetic",
             "config": {"workload": args.workload + ": " + w["desc"], "agents_per_gpu": N, "agents_total": N * world,
                        "episodes_per_step": chunk, "n_episodes": n_ep, "eval_at": eval_at,
+                       "table_store": {1: "hbm", 2: "shared_memory"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)],
                        "eval_steps_executed_not_counted": eval_steps, "env_steps_per_s_incl_eval": (train_steps + eval_steps) / (ms_max * 1e-3),
                        "l2": "inputs larger than L2: %.2f GB of per-agent tables per GPU vs 126 MB L2 (no flush needed)" % (table_bytes / 1e9),
                        "parallelism": "agents sharded by global id, %d per GPU; one NCCL gather of [episodes,4] metrics per step" % N,

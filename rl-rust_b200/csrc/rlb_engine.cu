@@ -50,6 +50,8 @@ struct rlb_engine {
     uint32_t S = 0, A = 0, APAD = 0, T = 1;
     size_t real_size = 4;
     Variant variant{};
+    int store = STORE_GLOBAL;          // where k_run keeps the tables: HBM or shared memory
+    size_t smem_bytes = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     DevParams dp{};
@@ -145,11 +147,35 @@ cudaError_t fill_q_default(rlb_engine* e) {
 
 cudaError_t dispatch_run(rlb_engine* e, const DevParams& p) {
     switch (e->cfg.env_kind) {
-        case RLB_ENV_BLACKJACK: return launch_run<RLB_ENV_BLACKJACK>(e->variant, p, e->stream);
-        case RLB_ENV_FROZEN_LAKE: return launch_run<RLB_ENV_FROZEN_LAKE>(e->variant, p, e->stream);
-        case RLB_ENV_CLIFF_WALKING: return launch_run<RLB_ENV_CLIFF_WALKING>(e->variant, p, e->stream);
-        default: return launch_run<RLB_ENV_TAXI>(e->variant, p, e->stream);
+        case RLB_ENV_BLACKJACK: return launch_run<RLB_ENV_BLACKJACK>(e->variant, p, e->store, e->stream);
+        case RLB_ENV_FROZEN_LAKE: return launch_run<RLB_ENV_FROZEN_LAKE>(e->variant, p, e->store, e->stream);
+        case RLB_ENV_CLIFF_WALKING: return launch_run<RLB_ENV_CLIFF_WALKING>(e->variant, p, e->store, e->stream);
+        default: return launch_run<RLB_ENV_TAXI>(e->variant, p, e->store, e->stream);
     }
+}
+
+// Where k_run keeps the per-agent tables.  The shared-memory (thread-group) store pays when every step sweeps many
+// rows, i.e. for the eligibility-trace agents of the 4-action envs; one-step updates touch two rows per step and run
+// faster from HBM at full occupancy (measured).
+rlb_status pick_store(rlb_engine* e) {
+    size_t bytes = 0;
+    switch (e->cfg.env_kind) {
+        case RLB_ENV_BLACKJACK: bytes = smem_store_bytes<RLB_ENV_BLACKJACK>(e->variant, e->S, e->dp.vmax); break;
+        case RLB_ENV_FROZEN_LAKE: bytes = smem_store_bytes<RLB_ENV_FROZEN_LAKE>(e->variant, e->S, e->dp.vmax); break;
+        case RLB_ENV_CLIFF_WALKING: bytes = smem_store_bytes<RLB_ENV_CLIFF_WALKING>(e->variant, e->S, e->dp.vmax); break;
+        default: bytes = smem_store_bytes<RLB_ENV_TAXI>(e->variant, e->S, e->dp.vmax); break;
+    }
+    const size_t per_block_max = 227 * 1024, per_sm = 228 * 1024;
+    const bool fits = bytes > 0 && bytes <= per_block_max;
+    e->smem_bytes = bytes;
+    if (e->cfg.store_kind == 1) { e->store = STORE_GLOBAL; return RLB_OK; }
+    if (e->cfg.store_kind == 2) {
+        if (!fits) { set_error("store_kind = shared memory, but this configuration needs %zu bytes per 8 agents (max %zu) or the env is not compiled for it", bytes, per_block_max); return RLB_ERR_UNSUPPORTED; }
+        e->store = STORE_SMEM;
+        return RLB_OK;
+    }
+    e->store = (fits && e->variant.trace && 4 * (bytes + 1024) <= per_sm) ? STORE_SMEM : STORE_GLOBAL;
+    return RLB_OK;
 }
 cudaError_t dispatch_step(rlb_engine* e, StepOp op, const StepArgs& a) {
     switch (e->cfg.env_kind) {
@@ -328,6 +354,8 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     CKE(fill<uint8_t>(e, e->d_flag, N, (uint8_t)1));   // policy_flag: true (double_tabular_policy.rs:23)
     rlb_status st = install_selector(e, cfg->selector_kind);
     if (st != RLB_OK) return fail(st);
+    st = pick_store(e);
+    if (st != RLB_OK) return fail(st);
     CKE(dispatch_step(e, OP_ENV_CONSTRUCT, StepArgs()));   // Env::new(): Blackjack deals a hand
     CKE(cudaStreamSynchronize(e->stream));
 #undef CKE
@@ -371,7 +399,7 @@ rlb_status rlb_engine_dims(const rlb_engine* e, uint32_t* n_states, uint32_t* n_
     if (n_tables) *n_tables = e->T;
     return RLB_OK;
 }
-uint32_t rlb_engine_store_kind(const rlb_engine* e) { return e ? 1u : 0u; }
+uint32_t rlb_engine_store_kind(const rlb_engine* e) { return e ? (uint32_t)e->store : 0u; }
 
 // ------------------------------------------------------------------------------- Env
 rlb_status rlb_env_reset(rlb_engine* e, uint32_t* obs_out) {
@@ -466,7 +494,9 @@ rlb_status rlb_agent_set_future_q_value_func(rlb_engine* e, int32_t target_kind)
 rlb_status rlb_agent_set_action_selector(rlb_engine* e, int32_t selector_kind) {
     if (!e || selector_kind < 0 || selector_kind > 1) { set_error("bad selector_kind"); return RLB_ERR_INVALID_ARG; }
     CK(cudaSetDevice(e->cfg.device));
-    return install_selector(e, selector_kind);
+    rlb_status st = install_selector(e, selector_kind);
+    if (st != RLB_OK) return st;
+    return pick_store(e);
 }
 
 rlb_status rlb_selector_reset(rlb_engine* e) {

@@ -38,8 +38,10 @@ enum StepOp {
     OP_SELECTOR_GET_ACTION, OP_SELECTOR_PROBS
 };
 
-template <int ENV> cudaError_t launch_run(const Variant& v, const DevParams& p, cudaStream_t stream);
+template <int ENV> cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStream_t stream);
+// bytes of dynamic shared memory one 32-agent CTA of the shared-memory store needs (0: env not compiled for it)
+template <int ENV> size_t smem_store_bytes(const Variant& v, uint32_t S, uint32_t vmax);
 template <int ENV> cudaError_t launch_step(StepOp op, const Variant& v, const DevParams& p, const StepArgs& a, cudaStream_t stream);
-template <int ENV> cudaError_t run_kernel_attributes(const Variant& v, cudaFuncAttributes* attr);
+template <int ENV> cudaError_t run_kernel_attributes(const Variant& v, int store, cudaFuncAttributes* attr);
 
 }   // namespace rlb

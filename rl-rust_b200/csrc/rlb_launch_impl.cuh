@@ -23,25 +23,66 @@ namespace rlb {
         case 13: CALL(double, 1, 0, true); break;                                      \
         case 14: CALL(double, 1, 1, false); break;                                     \
         case 15: CALL(double, 1, 1, true); break;                                      \
-        default: return cudaErrorInvalidValue;                                         \
+        default: break;                                                                \
     }
 
 constexpr int kBlock = 128;
 static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
+// shared-memory (thread-group) table store: compiled for the 4-action envs, whose whole per-agent working set is small
+template <int ENV> struct SmemCapable { static constexpr bool value = (ENV == RLB_ENV_FROZEN_LAKE || ENV == RLB_ENV_CLIFF_WALKING); };
+
 template <int ENV>
-cudaError_t launch_run(const Variant& v, const DevParams& p, cudaStream_t stream) {
+size_t smem_store_bytes(const Variant& v, uint32_t S, uint32_t vmax) {
+    if constexpr (!SmemCapable<ENV>::value) {
+        return 0;
+    } else {
+#define RLB_CALL(R, P, SL, T) return AgentCore<ENV, R, P, SL, T, STORE_SMEM>::SStore::bytes(S, vmax, SL == RLB_SEL_UCB, T) + EnvTab<ENV>::smem_bytes(S)
+        RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+        return 0;
+    }
+}
+
+template <int ENV>
+cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStream_t stream) {
+    if (store == STORE_SMEM) {
+        if constexpr (SmemCapable<ENV>::value) {
+            const unsigned grid = (unsigned)((p.n_agents + 7) / 8);   // one warp per CTA: 8 agents x 4 lanes
+            const size_t smem = smem_store_bytes<ENV>(v, p.S, p.vmax);
+#define RLB_CALL(R, P, SL, T)                                                                                          \
+    {                                                                                                                  \
+        auto kern = k_run<ENV, R, P, SL, T, STORE_SMEM>;                                                               \
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        if (err != cudaSuccess) return err;                                                                            \
+        kern<<<grid, 32, smem, stream>>>(p);                                                                           \
+    }
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            return cudaGetLastError();
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
     const unsigned grid = grid_for(p.n_agents);
     const size_t smem = EnvTab<ENV>::smem_bytes(p.S);
-#define RLB_CALL(R, P, S, T) k_run<ENV, R, P, S, T><<<grid, kBlock, smem, stream>>>(p)
+#define RLB_CALL(R, P, SL, T) k_run<ENV, R, P, SL, T, STORE_GLOBAL><<<grid, kBlock, smem, stream>>>(p)
     RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
     return cudaGetLastError();
 }
 
 template <int ENV>
-cudaError_t run_kernel_attributes(const Variant& v, cudaFuncAttributes* attr) {
-#define RLB_CALL(R, P, S, T) return cudaFuncGetAttributes(attr, k_run<ENV, R, P, S, T>)
+cudaError_t run_kernel_attributes(const Variant& v, int store, cudaFuncAttributes* attr) {
+    if (store == STORE_SMEM) {
+        if constexpr (SmemCapable<ENV>::value) {
+#define RLB_CALL(R, P, SL, T) return cudaFuncGetAttributes(attr, k_run<ENV, R, P, SL, T, STORE_SMEM>)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+        }
+        return cudaErrorInvalidValue;
+    }
+#define RLB_CALL(R, P, SL, T) return cudaFuncGetAttributes(attr, k_run<ENV, R, P, SL, T, STORE_GLOBAL>)
     RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
     return cudaSuccess;
@@ -99,8 +140,9 @@ cudaError_t launch_step(StepOp op, const Variant& v, const DevParams& p, const S
 }
 
 #define RLB_INSTANTIATE_ENV(ENV)                                                                         \
-    template cudaError_t launch_run<ENV>(const Variant&, const DevParams&, cudaStream_t);                \
+    template cudaError_t launch_run<ENV>(const Variant&, const DevParams&, int, cudaStream_t);           \
+    template size_t smem_store_bytes<ENV>(const Variant&, uint32_t, uint32_t);                           \
     template cudaError_t launch_step<ENV>(StepOp, const Variant&, const DevParams&, const StepArgs&, cudaStream_t); \
-    template cudaError_t run_kernel_attributes<ENV>(const Variant&, cudaFuncAttributes*);
+    template cudaError_t run_kernel_attributes<ENV>(const Variant&, int, cudaFuncAttributes*);
 
 }   // namespace rlb

@@ -72,9 +72,9 @@ def first_diff(a, b):
     return i, a[i], b[i], int(bad.sum())
 
 
-def gpu_run(c, h, n_agents, n_episodes, eval_at, first_agent_id=0, traj_capacity=0, chunks=None):
+def gpu_run(c, h, n_agents, n_episodes, eval_at, first_agent_id=0, traj_capacity=0, chunks=None, store_kind=0):
     """Train through the C ABI; returns dict of numpy arrays shaped like the oracle's batch output."""
-    with make_engine(c, h, n_agents, first_agent_id) as eng:
+    with make_engine(c, h, n_agents, first_agent_id, store_kind=store_kind) as eng:
         if chunks is None:
             res = eng.train(n_episodes, eval_at, sums=True, episodes=True, traj_capacity=traj_capacity)
             eps, sums = res["episodes"], res["sums"]

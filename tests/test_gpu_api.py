@@ -26,7 +26,7 @@ def test_step_trajectories_bit_exact(c):
     """Every env transition, chosen action, reward, termination flag and TD of every train / evaluate step."""
     n_agents, n_ep, eval_at = 6, 6, 3
     h = P.hyper(n_ep)
-    g = P.gpu_run(c, h, n_agents, n_ep, eval_at, traj_capacity=60000)
+    g = P.gpu_run(c, h, n_agents, n_ep, eval_at, traj_capacity=60000, store_kind=2 if c["env"] in (1, 2) else 1)
     cfg = P.oracle_config(c, h)
     for i in range(n_agents):
         s = O.Session(cfg, i)

@@ -19,8 +19,16 @@ def test_full_matrix(c):
     """4 envs x {one-step, traces} x {eps-greedy, UCB} x {Basic, Double} x 3 targets x {f32, f64}."""
     h = P.hyper(N_EPISODES)
     o = O.batch_train(P.oracle_config(c, h), 0, N_AGENTS, N_EPISODES, EVAL_AT, n_threads=8)
-    g = P.gpu_run(c, h, N_AGENTS, N_EPISODES, EVAL_AT)
-    P.compare(g, o, c)
+    # both table stores where the env is compiled for shared memory (FrozenLake, CliffWalking); HBM otherwise
+    stores = (1, 2) if c["env"] in (1, 2) else (1,)
+    for store in stores:
+        try:
+            g = P.gpu_run(c, h, N_AGENTS, N_EPISODES, EVAL_AT, store_kind=store)
+        except Exception as exc:                                  # noqa: BLE001
+            if store == 2 and getattr(exc, "status", None) == 5:  # RLB_ERR_UNSUPPORTED: 32 agents' working set > 227 KB
+                continue
+            raise
+        P.compare(g, o, c)
     # the per-episode reduction over agents is consistent with the raw stream
     assert np.array_equal(g["sums"][:, 0], g["len"].sum(0).astype(np.float64))
     assert np.array_equal(g["sums"][:, 1], g["ret"].sum(0))
