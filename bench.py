@@ -337,7 +337,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": args.real, "data": "synthetic",
             "config": {"workload": args.workload + ": " + w["desc"], "agents_per_gpu": N, "agents_total": N * world,
                        "episodes_per_step": chunk, "n_episodes": n_ep, "eval_at": eval_at,
-                       "table_store": {1: "hbm", 2: "shared_memory"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)],
+                       "table_store": {1: "hbm", 2: "shared_memory_groups", 3: "hybrid_smem_q_l2_traces"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)],
                        "eval_steps_executed_not_counted": eval_steps, "env_steps_per_s_incl_eval": (train_steps + eval_steps) / (ms_max * 1e-3),
                        "l2": "inputs larger than L2: %.2f GB of per-agent tables per GPU vs 126 MB L2 (no flush needed)" % (table_bytes / 1e9),
                        "parallelism": "agents sharded by global id, %d per GPU; one NCCL gather of [episodes,4] metrics per step" % N,

@@ -120,7 +120,8 @@ typedef struct rlb_config {
     uint64_t seed;               /* Philox key */
     uint64_t n_agents;           /* agents held by this engine */
     uint64_t first_agent_id;     /* global id of local agent 0 (Philox counter high words) */
-    uint32_t store_kind;         /* 0 = auto, 1 = tables in HBM, 2 = tables staged in shared memory */
+    uint32_t store_kind;         /* where the fused kernel keeps the tables: 0 = auto, 1 = HBM, 2 = shared memory (one agent per
+                                    4-lane thread group), 3 = hybrid (Q in shared memory, eligibility rows streamed through L2) */
     uint32_t reserved;
 } rlb_config;
 
@@ -188,7 +189,7 @@ rlb_status rlb_engine_set_stream(rlb_engine* e, void* cuda_stream);
 rlb_status rlb_engine_synchronize(rlb_engine* e);
 /* Env::action_size (env.rs:20-22) and the dense observation count */
 rlb_status rlb_engine_dims(const rlb_engine* e, uint32_t* n_states, uint32_t* n_actions, uint32_t* n_tables);
-/* which table store the engine picked (1 HBM, 2 shared memory) */
+/* which table store the engine picked (1 HBM, 2 shared memory thread groups, 3 hybrid) */
 uint32_t rlb_engine_store_kind(const rlb_engine* e);
 
 /* ---- Env<T,COUNT> (env.rs:19-49), batched ------------------------------------------------ */

@@ -60,6 +60,7 @@ struct rlb_engine {
     void* d_q = nullptr; size_t q_bytes = 0;
     uint32_t* d_counts = nullptr; size_t counts_bytes = 0;
     void* d_etr = nullptr;
+    void* d_etr_il = nullptr;   // warp-interleaved eligibility scratch of the hybrid store
     uint16_t* d_vis = nullptr;
     uint32_t* d_nvis = nullptr;
     uint64_t* d_rng_n = nullptr;
@@ -157,26 +158,46 @@ cudaError_t dispatch_run(rlb_engine* e, const DevParams& p) {
 // Where k_run keeps the per-agent tables.  The shared-memory (thread-group) store pays when every step sweeps many
 // rows, i.e. for the eligibility-trace agents of the 4-action envs; one-step updates touch two rows per step and run
 // faster from HBM at full occupancy (measured).
-rlb_status pick_store(rlb_engine* e) {
-    size_t bytes = 0;
+size_t store_bytes(rlb_engine* e, int store) {
     switch (e->cfg.env_kind) {
-        case RLB_ENV_BLACKJACK: bytes = smem_store_bytes<RLB_ENV_BLACKJACK>(e->variant, e->S, e->dp.vmax); break;
-        case RLB_ENV_FROZEN_LAKE: bytes = smem_store_bytes<RLB_ENV_FROZEN_LAKE>(e->variant, e->S, e->dp.vmax); break;
-        case RLB_ENV_CLIFF_WALKING: bytes = smem_store_bytes<RLB_ENV_CLIFF_WALKING>(e->variant, e->S, e->dp.vmax); break;
-        default: bytes = smem_store_bytes<RLB_ENV_TAXI>(e->variant, e->S, e->dp.vmax); break;
+        case RLB_ENV_BLACKJACK: return smem_store_bytes<RLB_ENV_BLACKJACK>(e->variant, store, e->S, e->dp.vmax);
+        case RLB_ENV_FROZEN_LAKE: return smem_store_bytes<RLB_ENV_FROZEN_LAKE>(e->variant, store, e->S, e->dp.vmax);
+        case RLB_ENV_CLIFF_WALKING: return smem_store_bytes<RLB_ENV_CLIFF_WALKING>(e->variant, store, e->S, e->dp.vmax);
+        default: return smem_store_bytes<RLB_ENV_TAXI>(e->variant, store, e->S, e->dp.vmax);
     }
+}
+
+rlb_status pick_store(rlb_engine* e) {
     const size_t per_block_max = 227 * 1024, per_sm = 228 * 1024;
-    const bool fits = bytes > 0 && bytes <= per_block_max;
-    e->smem_bytes = bytes;
-    if (e->cfg.store_kind == 1) { e->store = STORE_GLOBAL; return RLB_OK; }
-    if (e->cfg.store_kind == 2) {
-        if (!fits) { set_error("store_kind = shared memory, but this configuration needs %zu bytes per 8 agents (max %zu) or the env is not compiled for it", bytes, per_block_max); return RLB_ERR_UNSUPPORTED; }
-        e->store = STORE_SMEM;
-        return RLB_OK;
+    const size_t b_group = store_bytes(e, STORE_SMEM), b_hybrid = store_bytes(e, STORE_HYBRID);
+    const bool fits_group = b_group > 0 && b_group <= per_block_max;
+    const bool fits_hybrid = b_hybrid > 0 && b_hybrid <= per_block_max;
+    int want = e->cfg.store_kind;
+    if (want == 0) {
+        // measured: one-step updates touch two rows per step and run fastest from HBM at full occupancy;
+        // trace sweeps want the tables on chip.  Hybrid when >= 4 warps per SM fit, else the thread-group store.
+        want = STORE_GLOBAL;
+        if (e->variant.trace) {
+            if (fits_hybrid && 4 * (b_hybrid + 1024) <= per_sm) want = STORE_HYBRID;
+            else if (fits_group && 4 * (b_group + 1024) <= per_sm) want = STORE_SMEM;
+        }
+    } else if (want == STORE_SMEM && !fits_group) {
+        set_error("store_kind = shared memory (thread groups): needs %zu bytes per 8 agents (max %zu) or the env is not compiled for it", b_group, per_block_max);
+        return RLB_ERR_UNSUPPORTED;
+    } else if (want == STORE_HYBRID && !fits_hybrid) {
+        set_error("store_kind = hybrid: needs %zu bytes per 32 agents (max %zu) or the env is not compiled for it", b_hybrid, per_block_max);
+        return RLB_ERR_UNSUPPORTED;
     }
-    e->store = (fits && e->variant.trace && 4 * (bytes + 1024) <= per_sm) ? STORE_SMEM : STORE_GLOBAL;
+    e->store = want;
+    e->smem_bytes = want == STORE_SMEM ? b_group : (want == STORE_HYBRID ? b_hybrid : 0);
+    if (want == STORE_HYBRID && e->variant.trace && !e->d_etr_il) {
+        const uint64_t n32 = (e->cfg.n_agents + 31) / 32 * 32;
+        CK(cudaMalloc(&e->d_etr_il, (size_t)n32 * e->dp.vmax * e->APAD * e->real_size));
+        e->dp.etr_il = e->d_etr_il;
+    }
     return RLB_OK;
 }
+
 cudaError_t dispatch_step(rlb_engine* e, StepOp op, const StepArgs& a) {
     switch (e->cfg.env_kind) {
         case RLB_ENV_BLACKJACK: return launch_step<RLB_ENV_BLACKJACK>(op, e->variant, e->dp, a, e->stream);
@@ -249,7 +270,7 @@ bool valid_cfg(const rlb_config* c) {
         c->target_kind > 2 || c->agent_kind < 0 || c->agent_kind > 1 || c->real_kind < 0 || c->real_kind > 1 ||
         c->decay_kind < 0 || c->decay_kind > 1) { set_error("enum field out of range"); return false; }
     if (c->n_agents == 0) { set_error("n_agents must be > 0"); return false; }
-    if (c->store_kind > 2) { set_error("store_kind out of range"); return false; }
+    if (c->store_kind > 3) { set_error("store_kind out of range"); return false; }
     return true;
 }
 
@@ -334,7 +355,7 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     }
 
     DevParams& p = e->dp;
-    p.q = e->d_q; p.counts = nullptr; p.etr = e->d_etr; p.vis = e->d_vis; p.nvis = e->d_nvis;
+    p.q = e->d_q; p.counts = nullptr; p.etr = e->d_etr; p.etr_il = nullptr; p.vis = e->d_vis; p.nvis = e->d_nvis;
     p.rng_n = e->d_rng_n; p.eps = e->d_eps; p.ucb_t = e->d_ucb_t; p.flag = e->d_flag; p.env = e->d_env;
     p.trans = e->d_trans; p.thr = e->d_thr; p.thr_state = e->d_thr_state; p.n_thr = (uint32_t)e->tables.thr.size();
     p.slip_thr0 = e->tables.slip_thr0; p.slip_thr1 = e->tables.slip_thr1; p.slippery = cfg->slippery;
@@ -367,7 +388,7 @@ void rlb_engine_destroy(rlb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void* bufs[] = {e->d_q, e->d_counts, e->d_etr, e->d_vis, e->d_nvis, e->d_rng_n, e->d_eps, e->d_ucb_t, e->d_flag, e->d_env,
+    void* bufs[] = {e->d_q, e->d_counts, e->d_etr, e->d_etr_il, e->d_vis, e->d_nvis, e->d_rng_n, e->d_eps, e->d_ucb_t, e->d_flag, e->d_env,
                     e->d_trans, e->d_thr, e->d_thr_state, e->d_totals, e->d_flagword, e->d_episodes, e->d_sums};
     for (void* b : bufs) if (b) cudaFree(b);
     for (void* b : e->d_stage) if (b) cudaFree(b);

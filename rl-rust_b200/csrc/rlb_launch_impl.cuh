@@ -33,23 +33,47 @@ static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1)
 template <int ENV> struct SmemCapable { static constexpr bool value = (ENV == RLB_ENV_FROZEN_LAKE || ENV == RLB_ENV_CLIFF_WALKING); };
 
 template <int ENV>
-size_t smem_store_bytes(const Variant& v, uint32_t S, uint32_t vmax) {
+size_t smem_store_bytes(const Variant& v, int store, uint32_t S, uint32_t vmax) {
     if constexpr (!SmemCapable<ENV>::value) {
         return 0;
     } else {
-#define RLB_CALL(R, P, SL, T) return AgentCore<ENV, R, P, SL, T, STORE_SMEM>::SStore::bytes(S, vmax, SL == RLB_SEL_UCB, T) + EnvTab<ENV>::smem_bytes(S)
-        RLB_VARIANT_SWITCH(v, RLB_CALL)
+        if (store == STORE_HYBRID) {
+#define RLB_CALL(R, P, SL, T) return AgentCore<ENV, R, P, SL, T, STORE_HYBRID>::SStore::bytes(S, vmax, SL == RLB_SEL_UCB, T) + EnvTab<ENV>::smem_bytes(S)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
+        } else {
+#define RLB_CALL(R, P, SL, T) return AgentCore<ENV, R, P, SL, T, STORE_SMEM>::SStore::bytes(S, vmax, SL == RLB_SEL_UCB, T) + EnvTab<ENV>::smem_bytes(S)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+        }
         return 0;
     }
 }
 
 template <int ENV>
 cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStream_t stream) {
+    if (store == STORE_HYBRID) {
+        if constexpr (SmemCapable<ENV>::value) {
+            const unsigned grid = (unsigned)((p.n_agents + 31) / 32);   // one warp per CTA: 32 agents, one per lane
+            const size_t smem = smem_store_bytes<ENV>(v, store, p.S, p.vmax);
+#define RLB_CALL(R, P, SL, T)                                                                                          \
+    {                                                                                                                  \
+        auto kern = k_run<ENV, R, P, SL, T, STORE_HYBRID>;                                                             \
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        if (err != cudaSuccess) return err;                                                                            \
+        kern<<<grid, 32, smem, stream>>>(p);                                                                           \
+    }
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            return cudaGetLastError();
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
     if (store == STORE_SMEM) {
         if constexpr (SmemCapable<ENV>::value) {
             const unsigned grid = (unsigned)((p.n_agents + 7) / 8);   // one warp per CTA: 8 agents x 4 lanes
-            const size_t smem = smem_store_bytes<ENV>(v, p.S, p.vmax);
+            const size_t smem = smem_store_bytes<ENV>(v, store, p.S, p.vmax);
 #define RLB_CALL(R, P, SL, T)                                                                                          \
     {                                                                                                                  \
         auto kern = k_run<ENV, R, P, SL, T, STORE_SMEM>;                                                               \
@@ -74,6 +98,14 @@ cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStre
 
 template <int ENV>
 cudaError_t run_kernel_attributes(const Variant& v, int store, cudaFuncAttributes* attr) {
+    if (store == STORE_HYBRID) {
+        if constexpr (SmemCapable<ENV>::value) {
+#define RLB_CALL(R, P, SL, T) return cudaFuncGetAttributes(attr, k_run<ENV, R, P, SL, T, STORE_HYBRID>)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+        }
+        return cudaErrorInvalidValue;
+    }
     if (store == STORE_SMEM) {
         if constexpr (SmemCapable<ENV>::value) {
 #define RLB_CALL(R, P, SL, T) return cudaFuncGetAttributes(attr, k_run<ENV, R, P, SL, T, STORE_SMEM>)
@@ -141,7 +173,7 @@ cudaError_t launch_step(StepOp op, const Variant& v, const DevParams& p, const S
 
 #define RLB_INSTANTIATE_ENV(ENV)                                                                         \
     template cudaError_t launch_run<ENV>(const Variant&, const DevParams&, int, cudaStream_t);           \
-    template size_t smem_store_bytes<ENV>(const Variant&, uint32_t, uint32_t);                           \
+    template size_t smem_store_bytes<ENV>(const Variant&, int, uint32_t, uint32_t);                           \
     template cudaError_t launch_step<ENV>(StepOp, const Variant&, const DevParams&, const StepArgs&, cudaStream_t); \
     template cudaError_t run_kernel_attributes<ENV>(const Variant&, int, cudaFuncAttributes*);
 

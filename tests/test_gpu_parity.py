@@ -20,12 +20,12 @@ def test_full_matrix(c):
     h = P.hyper(N_EPISODES)
     o = O.batch_train(P.oracle_config(c, h), 0, N_AGENTS, N_EPISODES, EVAL_AT, n_threads=8)
     # both table stores where the env is compiled for shared memory (FrozenLake, CliffWalking); HBM otherwise
-    stores = (1, 2) if c["env"] in (1, 2) else (1,)
+    stores = (1, 2, 3) if c["env"] in (1, 2) else (1,)
     for store in stores:
         try:
             g = P.gpu_run(c, h, N_AGENTS, N_EPISODES, EVAL_AT, store_kind=store)
         except Exception as exc:                                  # noqa: BLE001
-            if store == 2 and getattr(exc, "status", None) == 5:  # RLB_ERR_UNSUPPORTED: 32 agents' working set > 227 KB
+            if store in (2, 3) and getattr(exc, "status", None) == 5:  # RLB_ERR_UNSUPPORTED: 32 agents' working set > 227 KB
                 continue
             raise
         P.compare(g, o, c)
