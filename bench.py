@@ -167,7 +167,7 @@ def run_reference_arm(args, w, real):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_thread = 4
+    per_thread = 64   # agents per host thread: each reference step is then a few hundred ms of CPU work
     n_agents = cores * per_thread
     chunk, n_ep = w["chunk"], w["n_episodes"]
     sessions = None

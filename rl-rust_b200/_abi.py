@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librlb.so")
+LIB_PATH = os.environ.get("RLB_LIB", os.path.join(_HERE, "librlb.so"))   # RLB_LIB: A/B a differently built library
 
 OK, ERR_ENV_NOT_READY, ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = range(6)
 ENV_BLACKJACK, ENV_FROZEN_LAKE, ENV_CLIFF_WALKING, ENV_TAXI = range(4)
