@@ -355,7 +355,7 @@ def main():
                            "note": "C-ABI rlb_agent_train_range with pinned HOST buffers: per-agent episode records + per-episode sums copied "
                                    "device->host every step; the path has no per-step host inputs besides the call's scalar arguments"}
         if world == 1 and not args.no_cpu_baseline:
-            cpu_agents = 24
+            cpu_agents = 512   # ~10 s of single-thread CPU work for c2
             ts, dt, _ = cpu_sample(w, real, cpu_agents, 1, 0, n_ep)
             line["cpu_baseline"] = {"value": ts / dt, "unit": "agent-steps/s", "cores": 1, "kind": "port",
                                     "sample": "%d agents x one full %d-episode run (eval_at %d), C++ oracle single thread, %.1f s"

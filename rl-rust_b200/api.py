@@ -249,11 +249,12 @@ class _Agent:
     def train(self, env, n_episodes, eval_at, *, raw=False):
         """agent.rs:66-118.  Returns (reward_history, episode_length, training_error).
 
-        With n_agents == 1 these are the reference's three vectors exactly (training_error
-        per step).  With more agents, reward_history and episode_length are [n_agents,
-        n_episodes] arrays and training_error is the per-episode sum of TDs [n_agents,
-        n_episodes] (a per-step stream for millions of agents does not fit anywhere).
-        raw=True returns the engine's dict instead (per-episode sums over agents, counters).
+        reward_history and episode_length are the reference's vectors ([n_episodes] for one
+        agent, [n_agents, n_episodes] otherwise).  training_error is per EPISODE here — the sum
+        of the episode's temporal differences — because a per-step stream for millions of
+        agents does not fit anywhere; Engine.train(traj_capacity=...) taps the per-step TDs
+        (rlb_traj_record.td) for small runs.  raw=True returns the engine's dict instead
+        (per-episode sums over agents, step counters, kernel time).
         """
         if eval_at == 0:
             raise ZeroDivisionError("attempt to calculate the remainder with a divisor of zero")   # agent.rs:107
@@ -261,7 +262,6 @@ class _Agent:
         if raw:
             return self.engine.train(n_episodes, eval_at)
         if self.n_agents == 1:
-            cap = 0
             res = self.engine.train(n_episodes, eval_at, sums=False, episodes=True)
             ep = res["episodes"][:, 0]
             return ep["ret"].astype(np.float64), ep["length"].astype(np.uint64), ep["td_sum"].astype(np.float64)
