@@ -121,6 +121,19 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(workload, agents_per_gpu, dtype):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_run launch from the committed ncu capture of this exact
+    configuration (profiles/r01b_traffic.json); None when the run's configuration was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01b_traffic.json")) as f:
+            t = json.load(f).get(workload)
+        if t and t["agents_per_gpu"] == agents_per_gpu and t["dtype"] == dtype:
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def workload_hyper(w):
     import parity as P
     return P.hyper(w["n_episodes"], slippery=w.get("slippery", False))
@@ -345,7 +358,7 @@ def main():
             "clocks": clocks,
             "gpu_launches": int(dev["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_run", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(args.workload, N, args.real), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / n_launch, "launch_ms": dev["kernel_ms"] / n_launch,
                          "kernel_share_of_step": dev["kernel_ms"] / ms if ms > 0 else None},
         }
