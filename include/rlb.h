@@ -214,6 +214,11 @@ rlb_status rlb_agent_set_future_q_value_func(rlb_engine* e, int32_t target_kind)
 /* Agent::set_action_selector (agent.rs:50): installs a fresh selector built from cfg's
  * parameters (the reference clones a never-used selector, bin/taxi.rs:161). */
 rlb_status rlb_agent_set_action_selector(rlb_engine* e, int32_t selector_kind);
+/* A second agent object on the SAME env and RNG stream, as the bins build (bin/taxi.rs:138-156: a OneStepAgent and an
+ * ElegibilityTracesAgent, each with its own fresh policy, driven one after the other over one env).  Replaces the
+ * engine's agent by a freshly constructed one of `agent_kind`: default tables, policy_flag = true, a fresh selector of
+ * the current selector kind, no traces; the env state and the stream position carry on. */
+rlb_status rlb_agent_set_kind(rlb_engine* e, int32_t agent_kind);
 /* Agent::reset (one_step_agent.rs:43-46): selector.reset() + policy.reset() */
 rlb_status rlb_agent_reset(rlb_engine* e);
 /* Agent::train (agent.rs:66-118): the fused hot path.  All N agents run episodes

@@ -48,6 +48,7 @@ struct SessionBase {
     virtual void agent_reset() = 0;
     virtual void set_target(int kind) = 0;
     virtual void set_selector(int kind) = 0;
+    virtual void set_agent_kind(int kind) = 0;
     virtual void export_tables(double* q, u64* counts, OracleState* st) = 0;
     virtual u32 n_states() = 0;
     virtual u32 n_actions() = 0;
@@ -88,7 +89,20 @@ struct Session : SessionBase {
         return std::unique_ptr<ActionSelection<A, Real>>(new UpperConfidenceBound<A, Real>(cfg.ucb_c));
     }
     Session(const OracleConfig& c, u64 agent_id, Env<A>* e_) : cfg(c), rng(c.seed, agent_id, 0), env(e_) {}
+    // a second agent object over the same env and RNG stream (bin/taxi.rs:138-156)
+    void set_agent_kind(int kind) override {
+        cfg.agent_kind = kind;
+        basic = nullptr; dbl = nullptr;
+        build_agent();
+    }
     void finish_init() {
+        build_agent();
+        u32 S = env->n_states();
+        id_of_dense.resize(S);
+        if (cfg.env_kind == 0) id_of_dense = BlackJackEnv::id_table();
+        else for (u32 i = 0; i < S; ++i) id_of_dense[i] = i;
+    }
+    void build_agent() {
         std::unique_ptr<Policy<A, Real>> pol;
         if (cfg.policy_kind == 0) { basic = new TabularPolicy<A, Real>((Real)cfg.lr, (Real)cfg.default_q); pol.reset(basic); }
         else { dbl = new DoubleTabularPolicy<A, Real>((Real)cfg.lr, (Real)cfg.default_q); pol.reset(dbl); }
@@ -100,10 +114,6 @@ struct Session : SessionBase {
         else
             agent.reset(new ElegibilityTracesAgent<A, Real>(std::move(pol), (Real)cfg.gamma, std::move(sel),
                                                             (Real)cfg.lambda, target_fn(cfg.target_kind)));
-        u32 S = env->n_states();
-        id_of_dense.resize(S);
-        if (cfg.env_kind == 0) id_of_dense = BlackJackEnv::id_table();
-        else for (u32 i = 0; i < S; ++i) id_of_dense[i] = i;
     }
     int train(u64 ep_begin, u64 ep_end, u64 eval_at, double* ret, u64* len, double* tdsum, double* tdabs) override {
         std::vector<Real> r, te; std::vector<u64> l;
@@ -237,6 +247,7 @@ int oracle_evaluate(void* h, uint64_t n, double* ret, uint64_t* len) { return ((
 void oracle_agent_reset(void* h) { ((SessionBase*)h)->agent_reset(); }
 void oracle_set_target(void* h, int kind) { ((SessionBase*)h)->set_target(kind); }
 void oracle_set_selector(void* h, int kind) { ((SessionBase*)h)->set_selector(kind); }
+void oracle_set_agent_kind(void* h, int kind) { ((SessionBase*)h)->set_agent_kind(kind); }
 void oracle_export(void* h, double* q, uint64_t* counts, OracleState* st) { ((SessionBase*)h)->export_tables(q, counts, st); }
 uint64_t oracle_training_error_len(void* h) { return ((SessionBase*)h)->training_error.size(); }
 void oracle_training_error_copy(void* h, double* out) {

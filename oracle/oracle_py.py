@@ -72,6 +72,7 @@ def lib():
         L.oracle_agent_reset.argtypes = [vp]
         L.oracle_set_target.argtypes = [vp, i32]
         L.oracle_set_selector.argtypes = [vp, i32]
+        L.oracle_set_agent_kind.argtypes = [vp, i32]
         L.oracle_export.argtypes = [vp, vp, vp, P(OracleState)]
         L.oracle_training_error_len.restype = u64
         L.oracle_training_error_len.argtypes = [vp]
@@ -187,6 +188,9 @@ class Session:
 
     def set_selector(self, k):
         self.L.oracle_set_selector(self.h, k)
+
+    def set_agent_kind(self, k):
+        self.L.oracle_set_agent_kind(self.h, k)
 
     def export(self):
         q = np.zeros((self.T, self.S, self.A), np.float64)

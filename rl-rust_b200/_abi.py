@@ -58,7 +58,7 @@ EXPORTS = [
     "rlb_abi_version", "rlb_last_error_string", "rlb_device_count", "rlb_engine_create", "rlb_engine_destroy",
     "rlb_engine_set_stream", "rlb_engine_synchronize", "rlb_engine_dims", "rlb_engine_store_kind", "rlb_env_reset",
     "rlb_env_step", "rlb_agent_get_action", "rlb_agent_update", "rlb_agent_set_future_q_value_func",
-    "rlb_agent_set_action_selector", "rlb_agent_reset", "rlb_agent_train", "rlb_agent_train_range",
+    "rlb_agent_set_action_selector", "rlb_agent_set_kind", "rlb_agent_reset", "rlb_agent_train", "rlb_agent_train_range",
     "rlb_agent_evaluate", "rlb_policy_predict", "rlb_policy_get_values", "rlb_policy_update",
     "rlb_policy_after_update", "rlb_policy_reset", "rlb_selector_get_action", "rlb_selector_get_exploration_probs",
     "rlb_selector_update", "rlb_selector_reset", "rlb_download_tables", "rlb_upload_tables", "rlb_get_agent_states",
@@ -103,6 +103,7 @@ def _load():
     L.rlb_agent_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.rlb_agent_set_future_q_value_func.argtypes = [vp, i32]
     L.rlb_agent_set_action_selector.argtypes = [vp, i32]
+    L.rlb_agent_set_kind.argtypes = [vp, i32]
     L.rlb_agent_reset.argtypes = [vp]
     L.rlb_agent_train.argtypes = [vp, u64, u64, P(RlbTrainOut)]
     L.rlb_agent_train_range.argtypes = [vp, u64, u64, u64, P(RlbTrainOut)]
@@ -254,6 +255,9 @@ class Engine:
 
     def set_selector(self, kind):
         check(lib.rlb_agent_set_action_selector(self.h, kind))
+
+    def set_agent_kind(self, kind):
+        check(lib.rlb_agent_set_kind(self.h, kind))
 
     def agent_reset(self):
         check(lib.rlb_agent_reset(self.h))

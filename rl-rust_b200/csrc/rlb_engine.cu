@@ -520,6 +520,27 @@ rlb_status rlb_agent_set_action_selector(rlb_engine* e, int32_t selector_kind) {
     return pick_store(e);
 }
 
+rlb_status rlb_agent_set_kind(rlb_engine* e, int32_t agent_kind) {
+    if (!e || agent_kind < 0 || agent_kind > 1) { set_error("bad agent_kind"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    e->cfg.agent_kind = agent_kind;
+    e->variant.trace = agent_kind == RLB_AGENT_TRACES ? 1 : 0;
+    if (e->variant.trace && !e->d_etr) {
+        const uint64_t by_steps = e->cfg.env_kind == RLB_ENV_BLACKJACK ? 32ull : (uint64_t)e->cfg.max_steps + 1ull;
+        const uint32_t vmax = (uint32_t)std::min<uint64_t>(e->S, by_steps);
+        CK(cudaMalloc(&e->d_etr, (size_t)N * vmax * e->APAD * e->real_size));
+        CK(cudaMalloc(&e->d_vis, (size_t)N * vmax * sizeof(uint16_t)));
+        e->dp.etr = e->d_etr; e->dp.vis = e->d_vis; e->dp.vmax = vmax;
+    }
+    CK(fill_q_default(e));
+    CK(fill<uint8_t>(e, e->d_flag, N, (uint8_t)1));
+    CK(cudaMemsetAsync(e->d_nvis, 0, N * sizeof(uint32_t), e->stream));
+    rlb_status st = install_selector(e, e->cfg.selector_kind);
+    if (st != RLB_OK) return st;
+    return pick_store(e);
+}
+
 rlb_status rlb_selector_reset(rlb_engine* e) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
     CK(cudaSetDevice(e->cfg.device));

@@ -1,0 +1,143 @@
+"""Host experiment driver — the reference's per-env bins over the engine ("next" row N1/N2 of SURVEY.md §8f).
+
+`run_experiment()` is `main()` of src/bin/{taxi,frozen_lake,cliffwalking,blackjack}.rs with the same flags and
+defaults (bin/taxi.rs:22-68): two agents (OneStepAgent, ElegibilityTracesAgent) x two selectors (eps-greedy, UCB) x
+three bootstrap targets = 12 runs, each `train(n, n/10)` -> `evaluate(n)` -> `agent.reset()` (bin/taxi.rs:158-203), the
+env shared and never re-created, Blackjack followed by its win / loss / draw tally (bin/blackjack.rs:179-207).  The
+curves are `moving_average` (utils.rs:78-93, quirk included) of the per-episode MEAN over the batch's agents; they are
+returned / written as JSON — the plotters PNGs (utils.rs:97-157) are out of scope.
+
+With n_agents = 1 the reward and length curves are the reference's, value for value (same Philox stream).  The
+"Training Error" curve is windowed over episodes (mean TD per step of each episode), not over raw steps as in the
+reference (bin/taxi.rs:170-174): the per-step stream is only tapped for small runs.
+"""
+import json
+import time
+
+import numpy as np
+
+from . import _abi as abi
+from . import api
+
+LEGENDS = ["ε-Greedy One-Step Sarsa", "ε-Greedy One-Step Qlearning", "ε-Greedy One-Step Expected Sarsa", "UCB One-Step Sarsa",
+           "UCB One-Step Qlearning", "UCB One-Step Expected Sarsa", "ε-Greedy Trace Sarsa", "ε-Greedy Trace Qlearning",
+           "ε-Greedy Trace Expected Sarsa", "UCB Trace Sarsa", "UCB Trace Qlearning", "UCB Trace Expected Sarsa"]   # bin/taxi.rs:96-110
+
+DEFAULTS = dict(n_episodes=100000, max_steps=100, learning_rate=0.05, initial_epsilon=1.0, exploration_time=0.5, final_epsilon=0.0,
+                confidence_level=0.5, discount_factor=0.95, lambda_factor=0.5, moving_average_window=100, stochastic_env=False,
+                map="4x4")
+
+
+def moving_average(window, vector):
+    """utils.rs:78-93: sums of consecutive `window`-long slices, each divided by `window` — including the last,
+    possibly shorter, slice (the reference's quirk); when len % window == 0 there is no short slice."""
+    vector = np.asarray(vector, np.float64)
+    out = []
+    aux = 0
+    while aux < len(vector):
+        end = aux + window if aux + window < len(vector) else len(vector)
+        out.append(float(np.sum(vector[aux:end])) / float(window))
+        aux = end
+    return out
+
+
+def make_env(name, **flags):
+    if name == "blackjack":
+        return api.BlackJackEnv()                                                                    # bin/blackjack.rs:78
+    if name == "frozen_lake":
+        m = api.FrozenLakeEnv.MAP_4X4 if flags.get("map", "4x4") == "4x4" else api.FrozenLakeEnv.MAP_8X8   # bin/frozen_lake.rs:93-97
+        return api.FrozenLakeEnv(m, flags.get("stochastic_env", False), flags["max_steps"])
+    if name in ("cliffwalking", "cliff_walking"):
+        return api.CliffWalkingEnv(flags["max_steps"])
+    if name == "taxi":
+        return api.TaxiEnv(flags["max_steps"])
+    raise ValueError("unknown env %r" % name)
+
+
+def run_experiment(env_name, *, n_agents=1, seed=0x5EED0001, real="f64", device=0, tally_games=1000000, policy="basic",
+                   verbose=True, **flags):
+    """Returns {'legends', 'train_rewards', 'train_episodes_length', 'train_errors', 'test_rewards',
+    'test_episodes_length', 'seconds', ['blackjack_rates']} — the five chart series of bin/taxi.rs:205-223."""
+    f = dict(DEFAULTS)
+    f.update(flags)
+    n = int(f["n_episodes"])
+    epsilon_decay = f["initial_epsilon"] / (f["exploration_time"] * n)                               # bin/taxi.rs:78
+    window = max(1, n // int(f["moving_average_window"]))                                            # first argument at every call site
+    env = make_env(env_name, **f)
+    # ONE engine = the bins' one env + one RNG stream per agent slot; the two agent objects of bin/taxi.rs:138-156 take
+    # turns on it (rlb_agent_set_kind), so run 7 continues the stream where run 6 left it, as in the reference.
+    eng = abi.Engine(env.kind, n_agents=n_agents, policy=abi.POLICY_BASIC if policy == "basic" else abi.POLICY_DOUBLE,   # bins: Basic (bin/taxi.rs:126)
+                     selector=abi.SEL_EPS_GREEDY, target=abi.TARGET_SARSA, agent=abi.AGENT_ONE_STEP,
+                     real=abi.REAL_F32 if real == "f32" else abi.REAL_F64, learning_rate=f["learning_rate"],
+                     discount_factor=f["discount_factor"], lambda_factor=f["lambda_factor"], initial_epsilon=f["initial_epsilon"],
+                     decay_kind=abi.DECAY_SUB, epsilon_decay=epsilon_decay, final_epsilon=f["final_epsilon"],
+                     confidence_level=f["confidence_level"], default_value=0.0, seed=seed, device=device, **env._cfg())
+    env.bind(eng)
+    out = dict(legends=LEGENDS, train_rewards=[], train_episodes_length=[], train_errors=[], test_rewards=[],
+               test_episodes_length=[], seconds=[], train_steps=[])
+    if env_name == "blackjack":
+        out["blackjack_rates"] = []
+    i = 0
+    for agent_kind in (abi.AGENT_ONE_STEP, abi.AGENT_TRACES):                                        # bin/taxi.rs:154-159
+        eng.set_agent_kind(agent_kind)
+        for sel in (abi.SEL_EPS_GREEDY, abi.SEL_UCB):
+            eng.set_selector(sel)                                                                    # bin/taxi.rs:161 (a fresh clone)
+            for func in (api.sarsa, api.qlearning, api.expected_sarsa):
+                eng.set_target(func)                                                                 # bin/taxi.rs:163
+                t0 = time.perf_counter()
+                res = eng.train(n, max(1, n // 10))                                                  # bin/taxi.rs:165-166
+                dt = time.perf_counter() - t0
+                if verbose:
+                    print("%s %.2fs (%d agents, %.3g train steps/s)" % (LEGENDS[i], dt, n_agents, res["train_steps"] / dt))
+                s_ = res["sums"]                                                                     # [n,4]: sum len, ret, td, |td|
+                mean_len, mean_ret = s_[:, 0] / n_agents, s_[:, 1] / n_agents
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    mean_td = s_[:, 2] / s_[:, 0]
+                out["train_errors"].append(moving_average(window, mean_td))
+                out["train_rewards"].append(moving_average(window, mean_ret))
+                out["train_episodes_length"].append(moving_average(window, mean_len))
+                out["seconds"].append(dt)
+                out["train_steps"].append(int(res["train_steps"]))
+                if env_name == "blackjack" and tally_games:                                          # bin/blackjack.rs:179-207
+                    ev = eng.evaluate(int(tally_games), sums=False, episodes=True)["episodes"]["ret"]
+                    tot = float(ev.size)
+                    rates = (float((ev == 1.0).sum()) / tot, float((ev == -1.0).sum()) / tot, float(((ev != 1.0) & (ev != -1.0)).sum()) / tot)
+                    out["blackjack_rates"].append(rates)
+                    if verbose:
+                        print("%s has win-rate of %s%%, loss-rate of %s%% and draw-rate %s%%" % ((LEGENDS[i],) + rates))
+                ev = eng.evaluate(n, sums=True)["sums"]                                              # bin/taxi.rs:188
+                out["test_rewards"].append(moving_average(window, ev[:, 1] / n_agents))
+                out["test_episodes_length"].append(moving_average(window, ev[:, 0] / n_agents))
+                i += 1
+                eng.agent_reset()                                                                    # bin/taxi.rs:200
+    out["final_rng_n"] = [int(x) for x in eng.states()["rng_n"][:8]]
+    eng.close()
+    return out
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(description="RL-Rust bins over the B200 engine: blackjack | frozen_lake | cliffwalking | taxi")
+    ap.add_argument("env", choices=["blackjack", "frozen_lake", "cliffwalking", "taxi"])
+    ap.add_argument("--n_episodes", "-n", type=int, default=DEFAULTS["n_episodes"])
+    for name in ("max_steps", "moving_average_window"):
+        ap.add_argument("--" + name, type=int, default=DEFAULTS[name])
+    for name in ("learning_rate", "initial_epsilon", "exploration_time", "final_epsilon", "confidence_level", "discount_factor",
+                 "lambda_factor"):
+        ap.add_argument("--" + name, type=float, default=DEFAULTS[name])
+    ap.add_argument("--stochastic_env", action="store_true")
+    ap.add_argument("--map", default="4x4")
+    ap.add_argument("--show_example", action="store_true", help="accepted for compatibility; rendering is out of scope")
+    ap.add_argument("--n_agents", type=int, default=1)
+    ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x5EED0001)
+    ap.add_argument("--real", choices=["f32", "f64"], default="f64")
+    ap.add_argument("--tally_games", type=int, default=1000000)
+    ap.add_argument("--out", default=None, help="write the chart series as JSON here")
+    a = vars(ap.parse_args(argv))
+    env_name, outp = a.pop("env"), a.pop("out")
+    a.pop("show_example")
+    res = run_experiment(env_name, **a)
+    if outp:
+        with open(outp, "w") as fh:
+            json.dump(res, fh)
+    return res

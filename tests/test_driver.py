@@ -1,0 +1,54 @@
+"""Host driver ("next" rows N1/N2): moving_average with the reference's short-last-chunk quirk (CPU), and the
+12-run CLI matrix on one env + one RNG stream against the oracle driven the same way (GPU)."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+
+
+def test_moving_average_quirk():
+    drv = importlib.import_module("rl-rust_b200.driver")
+    v = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0]
+    assert drv.moving_average(3, v) == [2.0, 5.0, 7.0 / 3.0]          # utils.rs:78-93: the short last slice is divided by the full window
+    assert drv.moving_average(7, v) == [4.0]
+    assert drv.moving_average(8, v) == [28.0 / 8.0]
+    assert drv.moving_average(2, [1.0, 3.0, 5.0, 7.0]) == [2.0, 6.0]
+    assert drv.moving_average(3, []) == []
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_name,env_kind", [("taxi", O.ENV_TAXI), ("frozen_lake", O.ENV_FROZEN_LAKE), ("blackjack", O.ENV_BLACKJACK)])
+def test_twelve_run_matrix_matches_oracle(env_name, env_kind):
+    """bin/taxi.rs:158-203 with n_agents = 1: every curve of every one of the 12 runs equals the oracle's, i.e. the two
+    agent objects really share one env and one stream."""
+    drv = importlib.import_module("rl-rust_b200.driver")
+    n, seed = 40, 0xFACE
+    flags = dict(n_episodes=n, moving_average_window=10, stochastic_env=True, map="8x8")
+    res = drv.run_experiment(env_name, n_agents=1, seed=seed, real="f64", tally_games=300, verbose=False, **flags)
+    cfg = O.make_config(env_kind, map_id=1, slippery=1, target=O.TARGET_SARSA, eps_decay=1.0 / (0.5 * n), seed=seed)
+    s = O.Session(cfg, 0)
+    window = n // 10
+    i = 0
+    for kind in (0, 1):
+        s.set_agent_kind(kind)
+        for sel in (0, 1):
+            s.set_selector(sel)
+            for tgt in (0, 1, 2):
+                s.set_target(tgt)
+                ret, ln, tds, _ = s.train(n, n // 10)
+                assert res["train_steps"][i] == int(ln.sum())
+                assert res["train_rewards"][i] == drv.moving_average(window, ret)
+                assert res["train_episodes_length"][i] == drv.moving_average(window, ln.astype(np.float64))
+                if env_name == "blackjack":
+                    eret, _ = s.evaluate(300)
+                    assert res["blackjack_rates"][i] == (float((eret == 1).sum()) / 300, float((eret == -1).sum()) / 300,
+                                                         float(((eret != 1) & (eret != -1)).sum()) / 300)
+                eret, eln = s.evaluate(n)
+                assert res["test_rewards"][i] == drv.moving_average(window, eret)
+                assert res["test_episodes_length"][i] == drv.moving_average(window, eln.astype(np.float64))
+                s.agent_reset()
+                i += 1
+    assert res["final_rng_n"][0] == s.export()[2].rng_n
+    s.close()

@@ -250,3 +250,42 @@ def test_full_size_properties(name, c, n_agents, n_ep):
         assert np.array_equal(part["state"]["rng_n"], st["rng_n"][first:first + 64])
         o = O.batch_train(P.oracle_config(c, h), first, 64, n_ep, eval_at, n_threads=8)
         P.compare(part, o, c)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("env", [1, 2, 3])
+@pytest.mark.parametrize("max_steps", [0, 1, 2])
+def test_truncation_edges(env, max_steps):
+    """max_steps = 0: every episode is the truncation pseudo-step alone (obs 0, terminated; Q2).  Trace agent, both
+    arithmetic modes, every table store the env supports."""
+    n_agents, n_ep = 33, 6            # one lane past a warp
+    for real in (0, 1):
+        c = dict(env=env, agent=1, selector=0, policy=0, target=1, real=real)
+        h = P.hyper(n_ep, max_steps=max_steps)
+        o = O.batch_train(P.oracle_config(c, h), 0, n_agents, n_ep, 2, n_threads=4)
+        assert o["len"].max() <= max_steps + 1
+        for store in ((1, 2, 3) if env in (1, 2) else (1,)):
+            g = P.gpu_run(c, h, n_agents, n_ep, 2, store_kind=store)
+            P.compare(g, o, c)
+
+
+def test_zero_episodes_and_single_agent(rlb):
+    with rlb.Engine(1, n_agents=1, agent=1, slippery=True) as eng:
+        r = eng.train(0, 5, sums=True, episodes=True)
+        assert r["train_steps"] == 0 and r["eval_steps"] == 0 and r["sums"].shape == (0, 4) and r["episodes"].shape == (0, 1)
+        assert eng.states()["rng_n"][0] == 0                      # nothing drawn
+        ev = eng.evaluate(0)
+        assert ev["steps"] == 0
+        r = eng.train(3, 2, sums=True, episodes=True)             # evaluate(100) after episodes 0 and 2
+        assert r["eval_episodes"] == 200 and r["train_steps"] == int(r["episodes"]["length"].sum())
+
+
+def test_blackjack_heavy_rng_paths():
+    """Blackjack draws u32 cards with rejection, so the stream goes odd and straddles the 8-word window: many agents,
+    both selectors, to hit the mid-step refill paths."""
+    for sel in (0, 1):
+        c = dict(env=0, agent=0, selector=sel, policy=0, target=1, real=1)
+        h = P.hyper(60)
+        o = O.batch_train(P.oracle_config(c, h), 5000, 512, 60, 6, n_threads=8)
+        g = P.gpu_run(c, h, 512, 60, 6, first_agent_id=5000)
+        P.compare(g, o, c)
