@@ -8,10 +8,11 @@ C ABI of include/rlb.h, built into librlb.so), `_abi.py` (ctypes binding) and `a
 """
 from . import _abi as abi
 from ._abi import Engine, EnvNotReady, RlbError
+from .snapshot import load_snapshot, save_snapshot
 from .api import (BlackJackEnv, CliffWalkingEnv, DoubleTabularPolicy, ElegibilityTracesAgent, Env, FrozenLakeEnv,
                   OneStepAgent, TabularPolicy, TaxiEnv, UniformEpsilonGreed, UpperConfidenceBound, expected_sarsa,
                   qlearning, sarsa)
 
-__all__ = ["abi", "Engine", "EnvNotReady", "RlbError", "BlackJackEnv", "CliffWalkingEnv", "DoubleTabularPolicy",
+__all__ = ["abi", "Engine", "save_snapshot", "load_snapshot", "EnvNotReady", "RlbError", "BlackJackEnv", "CliffWalkingEnv", "DoubleTabularPolicy",
            "ElegibilityTracesAgent", "Env", "FrozenLakeEnv", "OneStepAgent", "TabularPolicy", "TaxiEnv",
            "UniformEpsilonGreed", "UpperConfidenceBound", "expected_sarsa", "qlearning", "sarsa"]

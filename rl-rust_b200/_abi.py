@@ -252,12 +252,15 @@ class Engine:
 
     def set_target(self, kind):
         check(lib.rlb_agent_set_future_q_value_func(self.h, kind))
+        self.cfg.target_kind = kind
 
     def set_selector(self, kind):
         check(lib.rlb_agent_set_action_selector(self.h, kind))
+        self.cfg.selector_kind = kind
 
     def set_agent_kind(self, kind):
         check(lib.rlb_agent_set_kind(self.h, kind))
+        self.cfg.agent_kind = kind
 
     def agent_reset(self):
         check(lib.rlb_agent_reset(self.h))
