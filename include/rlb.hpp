@@ -1,0 +1,297 @@
+// include/rlb.hpp — header-only C++ mirror of the reference's trait surface for the hot path, over the C ABI
+// of rlb.h.  The reference is a Rust crate and Rust is not available in the build image, so this is the
+// compiled-language host side: same type names, constructor arguments, method names and error behaviour as
+// JohnVithor/RL-Rust (paths below are under its `src/`), so client code reads like code written against the crate.
+//
+//     rlrust::TaxiEnv env(100);                                                        // env/taxi.rs:57
+//     rlrust::TabularPolicy policy(0.05, 0.0);                                         // policy/tabular_policy.rs:15
+//     rlrust::UniformEpsilonGreed selector(1.0, rlrust::Decay::sub(2e-5), 0.0);        // action_selection/uniform_epsilon_greed.rs:31
+//     rlrust::OneStepAgent agent(policy, 0.95, selector, rlrust::qlearning);           // agent/one_step_agent.rs:16
+//     auto [reward_history, episode_length, training_error] = agent.train(env, 100000, 10000);   // agent.rs:66-118
+//
+// One Agent object = `batch.n_agents` independent reference agents, each on its own Philox stream (n_agents = 1 is the
+// reference's single trait object).  Differences forced by the device boundary: the epsilon-decay closure is
+// Decay::sub(k) / Decay::mul(k); observations are dense indices (BlackJackEnv::obs_id gives the fxhash id);
+// `training_error` is per episode (sum of the episode's TDs) — see rlb_train_out.traj for the per-step stream.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "rlb.h"
+
+namespace rlrust {
+
+struct EnvNotReady : std::runtime_error {   // env.rs:16-17
+    EnvNotReady() : std::runtime_error("EnvNotReady") {}
+};
+struct RlbError : std::runtime_error {
+    rlb_status status;
+    RlbError(rlb_status st, const std::string& what) : std::runtime_error(what), status(st) {}
+};
+inline void check(rlb_status st) {
+    if (st == RLB_OK) return;
+    if (st == RLB_ERR_ENV_NOT_READY) throw EnvNotReady();
+    throw RlbError(st, rlb_last_error_string());
+}
+
+// agent.rs:17-45 — GetNextQValue, passed by name
+enum GetNextQValue { sarsa = RLB_TARGET_SARSA, qlearning = RLB_TARGET_QLEARNING, expected_sarsa = RLB_TARGET_EXPECTED_SARSA };
+
+struct Decay {   // stands for the `Rc<dyn Fn(f64) -> f64>` of uniform_epsilon_greed.rs:14
+    rlb_decay_kind kind;
+    double k;
+    static Decay sub(double k) { return {RLB_DECAY_SUB, k}; }   // |a| a - k   (bin/taxi.rs:132)
+    static Decay mul(double k) { return {RLB_DECAY_MUL, k}; }   // |a| a * k   (bin/frozen_lake_neural.rs:181)
+};
+
+struct Batch {   // the RNG injection contract and the device placement: no counterpart in the reference
+    uint64_t n_agents = 1, seed = 0x5EED0001ull, first_agent_id = 0;
+    rlb_real_kind real = RLB_REAL_F64;   // the reference's own arithmetic
+    int device = 0;
+};
+
+class Engine {   // RAII over rlb_engine
+   public:
+    explicit Engine(const rlb_config& cfg) : cfg_(cfg) { check(rlb_engine_create(&cfg_, &e_)); }
+    ~Engine() { rlb_engine_destroy(e_); }
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+    rlb_engine* get() const { return e_; }
+    const rlb_config& config() const { return cfg_; }
+
+   private:
+    rlb_config cfg_;
+    rlb_engine* e_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------------- Env<T, COUNT>  (env.rs:19-49)
+class Env {
+   public:
+    virtual ~Env() = default;
+    virtual size_t action_size() const = 0;                                  // env.rs:20-22
+    virtual void describe(rlb_config& cfg) const = 0;
+    std::vector<uint32_t> reset() {                                          // env.rs:23
+        std::vector<uint32_t> obs(n());
+        check(rlb_env_reset(bound(), obs.data()));
+        return obs;
+    }
+    // env.rs:24 — throws EnvNotReady where the reference returns Err(EnvNotReady)
+    std::tuple<std::vector<uint32_t>, std::vector<double>, std::vector<uint8_t>> step(const std::vector<uint32_t>& action) {
+        std::vector<uint32_t> obs(n());
+        std::vector<double> reward(n());
+        std::vector<uint8_t> terminated(n());
+        check(rlb_env_step(bound(), action.data(), obs.data(), reward.data(), terminated.data(), nullptr));
+        return {obs, reward, terminated};
+    }
+    void bind(Engine* e) { engine_ = e; }
+    Engine* engine() const { return engine_; }
+
+   private:
+    rlb_engine* bound() const {
+        if (!engine_) throw std::logic_error("env is not bound to an engine yet (train an agent on it first)");
+        return engine_->get();
+    }
+    size_t n() const { return engine_ ? (size_t)engine_->config().n_agents : 0; }
+    Engine* engine_ = nullptr;
+};
+
+class BlackJackEnv : public Env {   // env/blackjack.rs:30-163
+   public:
+    BlackJackEnv() = default;
+    size_t action_size() const override { return 2; }
+    void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_BLACKJACK; }
+    static uint64_t obs_id(uint32_t dense) { return rlb_blackjack_obs_id(dense); }   // blackjack.rs:25-27
+    static uint32_t dense_index(uint64_t id) { return rlb_blackjack_dense_index(id); }
+};
+class FrozenLakeEnv : public Env {   // env/frozen_lake.rs:12-134
+   public:
+    enum Map { MAP_4X4 = 0, MAP_8X8 = 1 };
+    FrozenLakeEnv(Map map, bool is_slippery, uint32_t max_steps) : map_(map), slippery_(is_slippery), max_steps_(max_steps) {}
+    size_t action_size() const override { return 4; }
+    void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_FROZEN_LAKE; c.map_id = map_; c.slippery = slippery_; c.max_steps = max_steps_; }
+
+   private:
+    Map map_; bool slippery_; uint32_t max_steps_;
+};
+class CliffWalkingEnv : public Env {   // env/cliff_walking.rs:6-89
+   public:
+    explicit CliffWalkingEnv(uint32_t max_steps) : max_steps_(max_steps) {}
+    size_t action_size() const override { return 4; }
+    void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_CLIFF_WALKING; c.max_steps = max_steps_; }
+
+   private:
+    uint32_t max_steps_;
+};
+class TaxiEnv : public Env {   // env/taxi.rs:10-159
+   public:
+    explicit TaxiEnv(uint32_t max_steps) : max_steps_(max_steps) {}
+    size_t action_size() const override { return 6; }
+    void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_TAXI; c.max_steps = max_steps_; }
+
+   private:
+    uint32_t max_steps_;
+};
+
+// ---------------------------------------------------------------------------------- Policy<T, COUNT>  (policy.rs:15-25)
+struct TabularPolicy {   // policy/tabular_policy.rs:8-44
+    double learning_rate, default_value;
+    TabularPolicy(double lr, double dflt) : learning_rate(lr), default_value(dflt) {}
+    virtual ~TabularPolicy() = default;
+    virtual rlb_policy_kind kind() const { return RLB_POLICY_BASIC; }
+};
+struct DoubleTabularPolicy : TabularPolicy {   // policy/double_tabular_policy.rs:8-67
+    using TabularPolicy::TabularPolicy;
+    rlb_policy_kind kind() const override { return RLB_POLICY_DOUBLE; }
+};
+
+// ---------------------------------------------------------------------------------- ActionSelection<T, COUNT>
+struct ActionSelection {   // action_selection.rs:10-15
+    virtual ~ActionSelection() = default;
+    virtual rlb_selector_kind kind() const = 0;
+    virtual void describe(rlb_config& c) const = 0;
+};
+struct UniformEpsilonGreed : ActionSelection {   // action_selection/uniform_epsilon_greed.rs:8-80
+    double epsilon; Decay decay; double final_epsilon;
+    UniformEpsilonGreed(double eps, Decay d, double fin) : epsilon(eps), decay(d), final_epsilon(fin) {}
+    rlb_selector_kind kind() const override { return RLB_SEL_EPS_GREEDY; }
+    void describe(rlb_config& c) const override { c.initial_epsilon = epsilon; c.decay_kind = decay.kind; c.epsilon_decay = decay.k; c.final_epsilon = final_epsilon; }
+};
+struct UpperConfidenceBound : ActionSelection {   // action_selection/upper_confidence_bound.rs:9-68
+    double confidence_level;
+    explicit UpperConfidenceBound(double c) : confidence_level(c) {}
+    rlb_selector_kind kind() const override { return RLB_SEL_UCB; }
+    void describe(rlb_config& c) const override { c.confidence_level = confidence_level; }
+};
+
+// ---------------------------------------------------------------------------------- Agent<T, COUNT>  (agent.rs:47-164)
+using TrainResult = std::tuple<std::vector<double>, std::vector<uint64_t>, std::vector<double>>;   // rewards, lengths, errors
+using EvalResult = std::tuple<std::vector<double>, std::vector<uint64_t>>;
+
+class Agent {
+   public:
+    virtual ~Agent() { delete engine_; }
+    void set_future_q_value_func(GetNextQValue f) {                          // agent.rs:48
+        target_ = f;
+        if (engine_) check(rlb_agent_set_future_q_value_func(engine_->get(), f));
+    }
+    // agent.rs:50 — installs a fresh selector of that kind; call register_selector() before the first train() for
+    // every selector whose parameters the engine must know (the bins build both up front, bin/taxi.rs:129-136)
+    void set_action_selector(const ActionSelection& s) {
+        s.describe(cfg_);
+        cfg_.selector_kind = s.kind();
+        if (engine_) check(rlb_agent_set_action_selector(engine_->get(), s.kind()));
+    }
+    void register_selector(const ActionSelection& s) { s.describe(cfg_); }
+    std::vector<uint32_t> get_action(const std::vector<uint32_t>& obs) {     // agent.rs:52
+        std::vector<uint32_t> a(obs.size());
+        check(rlb_agent_get_action(need(), obs.data(), a.data()));
+        return a;
+    }
+    void reset() { if (engine_) check(rlb_agent_reset(engine_->get())); }    // agent.rs:64
+
+    // agent.rs:66-118.  [agent-major] vectors of n_agents * n_episodes entries (just n_episodes for one agent).
+    TrainResult train(Env& env, uint64_t n_episodes, uint64_t eval_at) {
+        if (eval_at == 0) throw std::domain_error("attempt to calculate the remainder with a divisor of zero");   // agent.rs:107
+        bind(env);
+        const uint64_t N = cfg_.n_agents;
+        rlb_train_out out{};
+        std::vector<rlb_episode_f64> e64;
+        std::vector<rlb_episode_f32> e32;
+        if (cfg_.real_kind == RLB_REAL_F64) { e64.resize(N * n_episodes); out.episodes = e64.data(); }
+        else { e32.resize(N * n_episodes); out.episodes = e32.data(); }
+        check(rlb_agent_train(engine_->get(), n_episodes, eval_at, &out));
+        last_ = out;
+        TrainResult r;
+        auto& [rew, len, err] = r;
+        rew.resize(N * n_episodes); len.resize(N * n_episodes); err.resize(N * n_episodes);
+        for (uint64_t ep = 0; ep < n_episodes; ++ep)
+            for (uint64_t a = 0; a < N; ++a) {   // engine layout is [episode][agent]
+                const uint64_t src = ep * N + a, dst = a * n_episodes + ep;
+                if (cfg_.real_kind == RLB_REAL_F64) { rew[dst] = e64[src].ret; len[dst] = e64[src].length; err[dst] = e64[src].td_sum; }
+                else { rew[dst] = e32[src].ret; len[dst] = e32[src].length; err[dst] = e32[src].td_sum; }
+            }
+        return r;
+    }
+    // agent.rs:120-141
+    EvalResult evaluate(Env& env, uint64_t n_episodes) {
+        bind(env);
+        const uint64_t N = cfg_.n_agents;
+        std::vector<rlb_episode_f64> e64;
+        std::vector<rlb_episode_f32> e32;
+        void* dst;
+        if (cfg_.real_kind == RLB_REAL_F64) { e64.resize(N * n_episodes); dst = e64.data(); }
+        else { e32.resize(N * n_episodes); dst = e32.data(); }
+        uint64_t steps = 0;
+        check(rlb_agent_evaluate(engine_->get(), n_episodes, dst, nullptr, &steps));
+        EvalResult r;
+        auto& [rew, len] = r;
+        rew.resize(N * n_episodes); len.resize(N * n_episodes);
+        for (uint64_t ep = 0; ep < n_episodes; ++ep)
+            for (uint64_t a = 0; a < N; ++a) {
+                const uint64_t src = ep * N + a, d = a * n_episodes + ep;
+                if (cfg_.real_kind == RLB_REAL_F64) { rew[d] = e64[src].ret; len[d] = e64[src].length; }
+                else { rew[d] = e32[src].ret; len[d] = e32[src].length; }
+            }
+        return r;
+    }
+    const rlb_train_out& last_train() const { return last_; }   // step totals, kernel time of the last train()
+    Engine* engine() const { return engine_; }
+
+   protected:
+    Agent(const TabularPolicy& policy, double discount_factor, const ActionSelection& selector, double lambda_factor,
+          GetNextQValue f, rlb_agent_kind kind, const Batch& b)
+        : target_(f) {
+        cfg_ = rlb_config{};
+        cfg_.struct_size = sizeof(rlb_config);
+        cfg_.policy_kind = policy.kind();
+        cfg_.learning_rate = policy.learning_rate;
+        cfg_.default_value = policy.default_value;
+        cfg_.discount_factor = discount_factor;
+        cfg_.lambda_factor = lambda_factor;
+        cfg_.agent_kind = kind;
+        cfg_.confidence_level = 0.5;   // bin/taxi.rs:54 default until a UCB selector says otherwise
+        cfg_.initial_epsilon = 1.0;
+        selector.describe(cfg_);
+        cfg_.selector_kind = selector.kind();
+        cfg_.real_kind = b.real; cfg_.device = b.device; cfg_.seed = b.seed; cfg_.n_agents = b.n_agents; cfg_.first_agent_id = b.first_agent_id;
+        cfg_.max_steps = 100;
+    }
+
+   private:
+    void bind(Env& env) {
+        if (engine_) {
+            if (env.engine() != engine_) throw std::logic_error("agent is already bound to another env");
+            return;
+        }
+        env.describe(cfg_);
+        cfg_.target_kind = target_;
+        engine_ = new Engine(cfg_);
+        env.bind(engine_);
+    }
+    rlb_engine* need() const {
+        if (!engine_) throw std::logic_error("agent is not bound yet: train or evaluate on an env first");
+        return engine_->get();
+    }
+    rlb_config cfg_;
+    GetNextQValue target_;
+    Engine* engine_ = nullptr;
+    rlb_train_out last_{};
+};
+
+class OneStepAgent : public Agent {   // agent/one_step_agent.rs:7-86
+   public:
+    OneStepAgent(const TabularPolicy& policy, double discount_factor, const ActionSelection& action_selection, GetNextQValue f,
+                 const Batch& batch = Batch())
+        : Agent(policy, discount_factor, action_selection, 0.0, f, RLB_AGENT_ONE_STEP, batch) {}
+};
+class ElegibilityTracesAgent : public Agent {   // agent/elegibility_traces_agent.rs:8-104
+   public:
+    ElegibilityTracesAgent(const TabularPolicy& policy, double discount_factor, const ActionSelection& action_selection,
+                           double lambda_factor, GetNextQValue f, const Batch& batch = Batch())
+        : Agent(policy, discount_factor, action_selection, lambda_factor, f, RLB_AGENT_TRACES, batch) {}
+};
+
+}   // namespace rlrust

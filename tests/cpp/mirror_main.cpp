@@ -1,0 +1,73 @@
+// tests/cpp/mirror_main.cpp — client code written against include/rlb.hpp the way it would be written against the
+// reference crate; prints what it gets so tests/test_cpp_mirror.py can compare with the oracle.
+#include <cinttypes>
+#include <cstdio>
+#include <cstring>
+
+#include "rlb.hpp"
+
+using namespace rlrust;
+
+static void dump(const char* tag, const std::vector<double>& v) {
+    std::printf("%s", tag);
+    for (double x : v) { uint64_t b; std::memcpy(&b, &x, 8); std::printf(" %016" PRIx64, b); }
+    std::printf("\n");
+}
+static void dump(const char* tag, const std::vector<uint64_t>& v) {
+    std::printf("%s", tag);
+    for (uint64_t x : v) std::printf(" %" PRIu64, x);
+    std::printf("\n");
+}
+
+int main(int argc, char** argv) {
+    const bool probe = argc > 1 && std::strcmp(argv[1], "probe") == 0;
+    try {
+        // --- bin/taxi.rs in miniature: n_episodes = 60, three agents on streams 0..2 of seed 0xC0DE
+        const uint64_t n_episodes = 60;
+        const double epsilon_decay = 1.0 / (0.5 * (double)n_episodes);                     // bin/taxi.rs:78
+        TaxiEnv env(100);
+        TabularPolicy policy(0.05, 0.0);
+        UniformEpsilonGreed eg(1.0, Decay::sub(epsilon_decay), 0.0);
+        UpperConfidenceBound ucb(0.5);
+        Batch batch;
+        batch.n_agents = 3; batch.seed = 0xC0DE;
+        OneStepAgent agent(policy, 0.95, eg, qlearning, batch);
+        agent.register_selector(ucb);
+        if (probe) {   // no GPU: the engine must refuse loudly
+            try { agent.train(env, 1, 1); } catch (const RlbError& e) { std::printf("probe status=%d %s\n", (int)e.status, e.what()); return 0; }
+            std::printf("probe unexpected success\n");
+            return 1;
+        }
+        try { agent.train(env, 5, 0); std::printf("A no-throw\n"); } catch (const std::domain_error&) { std::printf("A eval_at==0 -> domain_error\n"); }
+        auto [rewards, lengths, errors] = agent.train(env, n_episodes, n_episodes / 10);
+        dump("A.rewards", rewards); dump("A.lengths", lengths); dump("A.errors", errors);
+        auto [ev_rewards, ev_lengths] = agent.evaluate(env, 10);
+        dump("A.eval_rewards", ev_rewards); dump("A.eval_lengths", ev_lengths);
+        // the env on its own: terminated by evaluate() -> step() is Err(EnvNotReady); reset() revives it
+        try { env.step({0, 0, 0}); std::printf("A no-throw\n"); } catch (const EnvNotReady&) { std::printf("A step after termination -> EnvNotReady\n"); }
+        auto obs = env.reset();
+        auto act = agent.get_action(obs);
+        auto [obs2, rew2, term2] = env.step(act);
+        std::printf("A.step %u %u %u | %u %u %u | %.1f %.1f %.1f\n", obs[0], obs[1], obs[2], obs2[0], obs2[1], obs2[2], rew2[0], rew2[1], rew2[2]);
+        agent.reset();
+        agent.set_action_selector(ucb);
+        agent.set_future_q_value_func(expected_sarsa);
+        auto [r2, l2, e2] = agent.train(env, 20, 2);
+        dump("A2.lengths", l2); dump("A2.errors", e2);
+
+        // --- BASELINE config C2's objects, f32
+        FrozenLakeEnv lake(FrozenLakeEnv::MAP_8X8, true, 100);
+        Batch b2;
+        b2.n_agents = 40; b2.seed = 77; b2.real = RLB_REAL_F32;
+        UniformEpsilonGreed eg2(1.0, Decay::sub(1.0 / (0.5 * 20.0)), 0.0);
+        ElegibilityTracesAgent tracer(policy, 0.95, eg2, 0.5, sarsa, b2);
+        auto [r3, l3, e3] = tracer.train(lake, 20, 2);
+        std::printf("B.totals %" PRIu64 " %" PRIu64 " store=%u\n", tracer.last_train().train_steps, tracer.last_train().eval_steps,
+                    rlb_engine_store_kind(tracer.engine()->get()));
+        dump("B.lengths", l3);
+    } catch (const std::exception& e) {
+        std::printf("FAILED: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

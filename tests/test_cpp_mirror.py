@@ -1,0 +1,67 @@
+"""The C++ host-side mirror (include/rlb.hpp): a client program written like code against the reference crate is compiled
+with g++, linked with librlb.so and — on the GPU — its printed results compared bit for bit with the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity as P
+from oracle import oracle_py as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "mirror_main")
+
+
+def build():
+    libdir = os.path.join(ROOT, "rl-rust_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "mirror_main.cpp"), "-o", EXE, "-L", libdir, "-lrlb",
+                           "-Wl,-rpath," + libdir])
+
+
+def f64s(tokens):
+    return np.array([struct.unpack("<d", struct.pack("<Q", int(t, 16)))[0] for t in tokens], np.float64)
+
+
+def test_mirror_compiles_and_refuses_without_a_gpu(rlb):
+    build()
+    if rlb.abi.lib.rlb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    out = subprocess.check_output([EXE, "probe"], text=True)
+    assert out.startswith("probe status=3") and "no CPU path" in out
+
+
+@pytest.mark.gpu
+def test_mirror_results_equal_oracle():
+    build()
+    out = subprocess.check_output([EXE], text=True)
+    assert "FAILED" not in out and "no-throw" not in out
+    assert "A eval_at==0 -> domain_error" in out and "A step after termination -> EnvNotReady" in out
+    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l[0] in "AB" and "." in l.split()[0]}
+    n = 60
+    cfg = O.make_config(O.ENV_TAXI, target=O.TARGET_QLEARNING, eps_decay=1.0 / (0.5 * n), seed=0xC0DE)
+    sessions = [O.Session(cfg, i) for i in range(3)]
+    rew, ln, err = f64s(lines["A.rewards"]).reshape(3, n), np.array(lines["A.lengths"], np.uint64).reshape(3, n), f64s(lines["A.errors"]).reshape(3, n)
+    erew, eln = f64s(lines["A.eval_rewards"]).reshape(3, 10), np.array(lines["A.eval_lengths"], np.uint64).reshape(3, 10)
+    step = lines["A.step"]
+    for i, s in enumerate(sessions):
+        r, l, t, _ = s.train(n, n // 10)
+        assert np.array_equal(rew[i], r) and np.array_equal(ln[i], l) and P.bits_equal(err[i], t)
+        r, l = s.evaluate(10)
+        assert np.array_equal(erew[i], r) and np.array_equal(eln[i], l)
+        o = s.env_reset()
+        a = s.get_action(o)
+        o2, r2, _ = s.env_step(a)
+        assert int(step[i]) == o and int(step[4 + i]) == o2 and float(step[8 + i]) == r2
+        s.agent_reset(); s.set_selector(1); s.set_target(2)
+        r, l, t, _ = s.train(20, 2)
+        assert np.array_equal(np.array(lines["A2.lengths"], np.uint64).reshape(3, 20)[i], l)
+        assert P.bits_equal(f64s(lines["A2.errors"]).reshape(3, 20)[i], t)
+        s.close()
+    c = dict(env=1, agent=1, selector=0, policy=0, target=0, real=0)
+    o = O.batch_train(P.oracle_config(c, P.hyper(20, seed=77)), 0, 40, 20, 2, n_threads=4)
+    tot = next(l for l in out.splitlines() if l.startswith("B.totals")).split()
+    assert int(tot[1]) == o["train_steps"] and int(tot[2]) == o["eval_steps"] and tot[3] == "store=3"
+    assert np.array_equal(np.array(lines["B.lengths"], np.uint64).reshape(40, 20), o["len"])
