@@ -29,7 +29,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -38,8 +37,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-# reference CLI defaults (src/bin/taxi.rs:22-68)
-DEFAULTS = dict(lr=0.05, gamma=0.95, lambda_=0.5, eps0=1.0, eps_final=0.0, ucb_c=0.5, default_q=0.0, max_steps=100)
 
 WORKLOADS = {
     "c1": dict(desc="Blackjack one-step Q-learning, eps-greedy, Basic", env=0, agent=0, selector=0, policy=0, target=1,

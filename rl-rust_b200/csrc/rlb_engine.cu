@@ -41,7 +41,6 @@ rlb_status cuda_fail(cudaError_t err, const char* what) {
         if (err__ != cudaSuccess) return cuda_fail(err__, #call); \
     } while (0)
 
-template <int ENV> struct EnvTag {};
 
 }   // namespace
 
