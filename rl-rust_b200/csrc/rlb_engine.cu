@@ -159,10 +159,10 @@ cudaError_t dispatch_run(rlb_engine* e, const DevParams& p) {
 // faster from HBM at full occupancy (measured).
 size_t store_bytes(rlb_engine* e, int store) {
     switch (e->cfg.env_kind) {
-        case RLB_ENV_BLACKJACK: return smem_store_bytes<RLB_ENV_BLACKJACK>(e->variant, store, e->S, e->dp.vmax);
-        case RLB_ENV_FROZEN_LAKE: return smem_store_bytes<RLB_ENV_FROZEN_LAKE>(e->variant, store, e->S, e->dp.vmax);
-        case RLB_ENV_CLIFF_WALKING: return smem_store_bytes<RLB_ENV_CLIFF_WALKING>(e->variant, store, e->S, e->dp.vmax);
-        default: return smem_store_bytes<RLB_ENV_TAXI>(e->variant, store, e->S, e->dp.vmax);
+        case RLB_ENV_BLACKJACK: return smem_store_bytes<RLB_ENV_BLACKJACK>(e->variant, store, e->S, e->S, e->dp.vmax);
+        case RLB_ENV_FROZEN_LAKE: return smem_store_bytes<RLB_ENV_FROZEN_LAKE>(e->variant, store, store == STORE_HYBRID ? e->dp.n_live : e->S, e->S, e->dp.vmax);
+        case RLB_ENV_CLIFF_WALKING: return smem_store_bytes<RLB_ENV_CLIFF_WALKING>(e->variant, store, store == STORE_HYBRID ? e->dp.n_live : e->S, e->S, e->dp.vmax);
+        default: return smem_store_bytes<RLB_ENV_TAXI>(e->variant, store, e->S, e->S, e->dp.vmax);
     }
 }
 
@@ -363,6 +363,8 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     p.ucb_c = cfg->confidence_level; p.default_q = cfg->default_value;
     p.decay_kind = cfg->decay_kind; p.target = cfg->target_kind;
     p.max_steps = cfg->max_steps; p.S = e->S; p.vmax = vmax;
+    p.n_live = e->tables.n_live;
+    std::memcpy(p.row_lut, e->tables.row_lut, sizeof p.row_lut);
     p.seed = cfg->seed; p.first_agent = cfg->first_agent_id; p.n_agents = N;
     p.mode = 0; p.eval_episodes = 100; p.ep0 = p.ep1 = 0; p.eval_at = 1; p.n_eval = 0;
     p.episodes = nullptr; p.traj = nullptr; p.traj_cap = 0; p.traj_count = nullptr;

@@ -101,7 +101,7 @@ static bool build_frozen_lake(const rlb_config& cfg, EnvTables& t, std::string& 
         const char here = map[row][col];
         for (int a = 0; a < 4; ++a) {
             uint16_t* slot = &t.trans[((size_t)s * 4 + a) * 3];
-            if (here == 'G' || here == 'H') { slot[0] = pack_tr((uint32_t)s, 0, true); continue; }   // :75-76, never stepped from
+            if (here == 'G' || here == 'H') { slot[0] = pack_tr((uint32_t)s, 0, true); t.dead_cell[s] = 1; continue; }   // :75-76, never stepped from
             const int cand[3] = {(a + 3) % 4, a, (a + 1) % 4};   // :78 (usize wrap: (0-1)%4 == 3)
             const int n_slots = cfg.slippery ? 3 : 1;
             for (int i = 0; i < n_slots; ++i) {
@@ -122,15 +122,34 @@ static bool build_frozen_lake(const rlb_config& cfg, EnvTables& t, std::string& 
     return true;
 }
 
+// Which states can be a step's `curr_obs`: everything but the terminal cells (FrozenLake holes / goal, Cliff cells /
+// goal).  Terminal states are only ever OBSERVED (Agent::get_action on the last observation, agent.rs:89), never
+// updated, so a table store may keep just the live rows on chip.
+static void build_row_lut(const rlb_config& cfg, EnvTables& t) {
+    std::memset(t.row_lut, 0xFF, sizeof t.row_lut);
+    t.n_live = t.S;
+    if (t.S > 64) return;
+    uint32_t next = 0;
+    for (uint32_t s = 0; s < t.S; ++s) {
+        bool dead = false;
+        if (cfg.env_kind == RLB_ENV_FROZEN_LAKE) dead = t.dead_cell[s] != 0;
+        if (cfg.env_kind == RLB_ENV_CLIFF_WALKING) dead = s >= 37;
+        if (!dead) t.row_lut[s] = (uint8_t)next++;
+    }
+    t.n_live = next;
+}
+
 bool build_env_tables(const rlb_config& cfg, EnvTables& t, std::string& err) {
     t = EnvTables();
     switch (cfg.env_kind) {
-        case RLB_ENV_BLACKJACK: t.S = 1456; t.A = 2; return true;
+        case RLB_ENV_BLACKJACK: t.S = 1456; t.A = 2; t.n_live = t.S; std::memset(t.row_lut, 0xFF, sizeof t.row_lut); return true;
         case RLB_ENV_FROZEN_LAKE:
             if (cfg.map_id != 0 && cfg.map_id != 1) { err = "frozen lake: map_id must be 0 (4x4) or 1 (8x8)"; return false; }
-            return build_frozen_lake(cfg, t, err);
-        case RLB_ENV_CLIFF_WALKING: build_cliff(t); return true;
-        case RLB_ENV_TAXI: build_taxi(t); return true;
+            if (!build_frozen_lake(cfg, t, err)) return false;
+            build_row_lut(cfg, t);
+            return true;
+        case RLB_ENV_CLIFF_WALKING: build_cliff(t); build_row_lut(cfg, t); return true;
+        case RLB_ENV_TAXI: build_taxi(t); t.n_live = t.S; std::memset(t.row_lut, 0xFF, sizeof t.row_lut); return true;
     }
     err = "unknown env_kind";
     return false;

@@ -14,6 +14,9 @@ struct EnvTables {
     std::vector<uint64_t> thr;         // Taxi start thresholds (k-space)
     std::vector<uint16_t> thr_state;
     uint64_t slip_thr0 = 0, slip_thr1 = 0;
+    uint32_t n_live = 0;               // states an action is ever taken from
+    uint8_t row_lut[64];               // state -> compact live-row index, 0xFF for terminal states (S <= 64 only)
+    uint8_t dead_cell[64] = {0};       // FrozenLake: hole / goal cells
 };
 
 bool build_env_tables(const rlb_config& cfg, EnvTables& out, std::string& err);

@@ -33,16 +33,16 @@ static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1)
 template <int ENV> struct SmemCapable { static constexpr bool value = (ENV == RLB_ENV_FROZEN_LAKE || ENV == RLB_ENV_CLIFF_WALKING); };
 
 template <int ENV>
-size_t smem_store_bytes(const Variant& v, int store, uint32_t S, uint32_t vmax) {
+size_t smem_store_bytes(const Variant& v, int store, uint32_t rows, uint32_t S, uint32_t vmax) {
     if constexpr (!SmemCapable<ENV>::value) {
         return 0;
     } else {
         if (store == STORE_HYBRID) {
-#define RLB_CALL(R, P, SL, T) return AgentCore<ENV, R, P, SL, T, STORE_HYBRID>::SStore::bytes(S, vmax, SL == RLB_SEL_UCB, T) + EnvTab<ENV>::smem_bytes(S)
+#define RLB_CALL(R, P, SL, T) return AgentCore<ENV, R, P, SL, T, STORE_HYBRID>::SStore::bytes(rows, vmax, SL == RLB_SEL_UCB, T) + EnvTab<ENV>::smem_bytes(S)
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
         } else {
-#define RLB_CALL(R, P, SL, T) return AgentCore<ENV, R, P, SL, T, STORE_SMEM>::SStore::bytes(S, vmax, SL == RLB_SEL_UCB, T) + EnvTab<ENV>::smem_bytes(S)
+#define RLB_CALL(R, P, SL, T) return AgentCore<ENV, R, P, SL, T, STORE_SMEM>::SStore::bytes(rows, vmax, SL == RLB_SEL_UCB, T) + EnvTab<ENV>::smem_bytes(S)
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
         }
@@ -55,7 +55,7 @@ cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStre
     if (store == STORE_HYBRID) {
         if constexpr (SmemCapable<ENV>::value) {
             const unsigned grid = (unsigned)((p.n_agents + 31) / 32);   // one warp per CTA: 32 agents, one per lane
-            const size_t smem = smem_store_bytes<ENV>(v, store, p.S, p.vmax);
+            const size_t smem = smem_store_bytes<ENV>(v, store, p.n_live, p.S, p.vmax);
 #define RLB_CALL(R, P, SL, T)                                                                                          \
     {                                                                                                                  \
         auto kern = k_run<ENV, R, P, SL, T, STORE_HYBRID>;                                                             \
@@ -73,7 +73,7 @@ cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStre
     if (store == STORE_SMEM) {
         if constexpr (SmemCapable<ENV>::value) {
             const unsigned grid = (unsigned)((p.n_agents + 7) / 8);   // one warp per CTA: 8 agents x 4 lanes
-            const size_t smem = smem_store_bytes<ENV>(v, store, p.S, p.vmax);
+            const size_t smem = smem_store_bytes<ENV>(v, store, p.S, p.S, p.vmax);
 #define RLB_CALL(R, P, SL, T)                                                                                          \
     {                                                                                                                  \
         auto kern = k_run<ENV, R, P, SL, T, STORE_SMEM>;                                                               \
@@ -173,7 +173,7 @@ cudaError_t launch_step(StepOp op, const Variant& v, const DevParams& p, const S
 
 #define RLB_INSTANTIATE_ENV(ENV)                                                                         \
     template cudaError_t launch_run<ENV>(const Variant&, const DevParams&, int, cudaStream_t);           \
-    template size_t smem_store_bytes<ENV>(const Variant&, int, uint32_t, uint32_t);                           \
+    template size_t smem_store_bytes<ENV>(const Variant&, int, uint32_t, uint32_t, uint32_t);                           \
     template cudaError_t launch_step<ENV>(StepOp, const Variant&, const DevParams&, const StepArgs&, cudaStream_t); \
     template cudaError_t run_kernel_attributes<ENV>(const Variant&, int, cudaFuncAttributes*);
 
