@@ -120,9 +120,9 @@ def peaks():
 
 def measured_traffic(workload, agents_per_gpu, dtype):
     """dram__bytes_read.sum + dram__bytes_write.sum per k_run launch from the committed ncu capture of this exact
-    configuration (profiles/r01b_traffic.json); None when the run's configuration was not captured."""
+    configuration (profiles/traffic.json); None when the run's configuration was not captured."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01b_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f).get(workload)
         if t and t["agents_per_gpu"] == agents_per_gpu and t["dtype"] == dtype:
             return t["dram_bytes_per_launch"]
