@@ -174,10 +174,10 @@ rlb_status pick_store(rlb_engine* e) {
     int want = e->cfg.store_kind;
     if (want == 0) {
         // measured: one-step updates touch two rows per step and run fastest from HBM at full occupancy;
-        // trace sweeps want the tables on chip.  Hybrid when >= 4 warps per SM fit, else the thread-group store.
+        // trace sweeps want the tables on chip.  Hybrid when >= 3 warps per SM fit, else the thread-group store (>= 4).
         want = STORE_GLOBAL;
         if (e->variant.trace) {
-            if (fits_hybrid && 4 * (b_hybrid + 1024) <= per_sm) want = STORE_HYBRID;
+            if (fits_hybrid && 3 * (b_hybrid + 1024) <= per_sm) want = STORE_HYBRID;   // f64 C2 at 3 CTAs/SM: 4.2e9 vs 3.4e9 (groups, HBM)
             else if (fits_group && 4 * (b_group + 1024) <= per_sm) want = STORE_SMEM;
         }
     } else if (want == STORE_SMEM && !fits_group) {

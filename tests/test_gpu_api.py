@@ -289,3 +289,28 @@ def test_blackjack_heavy_rng_paths():
         o = O.batch_train(P.oracle_config(c, h), 5000, 512, 60, 6, n_threads=8)
         g = P.gpu_run(c, h, 512, 60, 6, first_agent_id=5000)
         P.compare(g, o, c)
+
+
+@pytest.mark.parametrize("name,c,n_ep,chunk", [("c2", dict(env=1, agent=1, selector=0, policy=0, target=0, real=0), 1000, 100),
+                                                ("c4", dict(env=3, agent=0, selector=0, policy=0, target=1, real=0), 1000, 100)])
+def test_bench_workload_full_length_sample(name, c, n_ep, chunk):
+    """Exactly what bench.py runs — the whole 1000-episode run (epsilon 1 -> 0, then greedy), driven in 100-episode
+    chunks with eval_at = n/10 — on 4096 agents; the first and last 24 agents are replayed by the oracle."""
+    n_agents = 4096
+    h = P.hyper(n_ep, slippery=True)
+    with P.make_engine(c, h, n_agents) as eng:
+        lens, tds = [], []
+        for b in range(0, n_ep, chunk):
+            r = eng.train(b + chunk, n_ep // 10, ep_begin=b, sums=False, episodes=True)
+            lens.append(r["episodes"]["length"]); tds.append(r["episodes"]["td_sum"])
+        length, tdsum = np.concatenate(lens, 0), np.concatenate(tds, 0)
+        st = eng.states()
+        q, _ = eng.download_tables(counts=False)
+    for first in (0, n_agents - 24):
+        o = O.batch_train(P.oracle_config(c, h), first, 24, n_ep, n_ep // 10, n_threads=8)
+        sl = slice(first, first + 24)
+        assert np.array_equal(length[:, sl].T, o["len"])
+        assert P.bits_equal(tdsum[:, sl].T.astype(np.float64), o["tdsum"])
+        assert P.bits_equal(q[sl].astype(np.float64), o["q"])
+        assert np.array_equal(st["rng_n"][sl], o["state"]["rng_n"]) and P.bits_equal(st["epsilon"][sl], o["state"]["epsilon"])
+    assert np.all(st["epsilon"] < 0.01)   # the schedule ran out: the last half of the run was (almost) greedy
