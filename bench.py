@@ -48,6 +48,12 @@ WORKLOADS = {
     "c4": dict(desc="Taxi one-step Q-learning, eps-greedy, Basic", env=3, agent=0, selector=0, policy=0, target=1,
                agents_per_gpu=1 << 21, n_episodes=1000, chunk=100),
 }
+# C5, the full sweep: 4 envs x {Sarsa, Q, Expected Sarsa one-step; Sarsa(lambda), Q(lambda)} x {eps-greedy, UCB} x
+# {Basic, Double} = 80 cells, every cell an engine of its own on every GPU, one metric gather per cell per step.
+WORKLOADS["c5"] = dict(desc="full sweep: 4 envs x 5 update rules x {eps-greedy, UCB} x {Basic, Double} = 80 cells", cells=[
+    dict(env=env, agent=agent, target=target, selector=sel, policy=pol, slippery=True)
+    for env in (0, 1, 2, 3) for (agent, target) in ((0, 0), (0, 1), (0, 2), (1, 0), (1, 1)) for sel in (0, 1) for pol in (0, 1)],
+    agents_per_gpu=8192, n_episodes=1000, chunk=100)
 A_OF_ENV = {0: 2, 1: 4, 2: 4, 3: 6}
 
 
@@ -177,18 +183,22 @@ def run_reference_arm(args, w, real):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_thread = 64   # agents per host thread: each reference step is then a few hundred ms of CPU work
+    cells = [dict(w, **c) for c in w["cells"]] if "cells" in w else [w]
+    per_thread = 64 if len(cells) == 1 else 1   # agents per host thread (per cell): each reference step is a few hundred ms of CPU work
     n_agents = cores * per_thread
     chunk, n_ep = w["chunk"], w["n_episodes"]
-    sessions = None
+    sessions = [None] * len(cells)
     k = 0
     times, steps = [], []
     for it in range(args.warmup + args.steps):
         c = k % (n_ep // chunk)
-        if c == 0 and k > 0:
-            for s in sessions:
-                s.agent_reset()
-        ts, dt, sessions = cpu_sample(w, real, n_agents, cores, c * chunk, (c + 1) * chunk, sessions)
+        ts, dt = 0, 0.0
+        for ci, cell in enumerate(cells):
+            if c == 0 and k > 0:
+                for s in sessions[ci]:
+                    s.agent_reset()
+            ts_, dt_, sessions[ci] = cpu_sample(cell, real, n_agents, cores, c * chunk, (c + 1) * chunk, sessions[ci])
+            ts += ts_; dt += dt_
         k += 1
         if it >= args.warmup:
             times.append(dt); steps.append(ts)
@@ -198,10 +208,11 @@ def run_reference_arm(args, w, real):
         "impl": "reference", "metric": "agent-env steps/sec (updates incl.)", "value": v, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if real else "f32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + w["desc"], "agents": n_agents, "episodes_per_step": chunk,
+        "config": {"workload": args.workload + ": " + w["desc"], "agents": n_agents * len(cells), "episodes_per_step": chunk,
                    "n_episodes": n_ep, "eval_at": n_ep // 10},
         "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d agents (%d per host thread) x %d-episode chunks of the same run; C++ oracle, hash-map tables" % (n_agents, per_thread, chunk)},
+                         "sample": "%d agents (%d per host thread%s) x %d-episode chunks of the same run; C++ oracle, hash-map tables"
+                                   % (n_agents * len(cells), per_thread, " per cell" if len(cells) > 1 else "", chunk)},
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -251,37 +262,43 @@ def main():
     chunk, n_ep = w["chunk"], w["n_episodes"]
     eval_at = max(1, n_ep // 10)
     chunks_per_run = n_ep // chunk
-    h = workload_hyper(w)
-    eng = P.make_engine(combo(w, real), h, N, first_agent_id=sh.shard(rank, N), device=local_rank, store_kind=args.store)
+    # one engine per cell (N agents each on this GPU); every workload but C5 is a single cell
+    cells = [dict(w, **c) for c in w["cells"]] if "cells" in w else [w]
     stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
-    apad = 8 if eng.A == 6 else eng.A
-    table_bytes = N * eng.S * eng.T * apad * real_size
+    engines = []
+    for cell in cells:
+        e_ = P.make_engine(combo(cell, real), workload_hyper(cell), N, first_agent_id=sh.shard(rank, N), device=local_rank,
+                           store_kind=args.store)
+        e_.set_stream(stream.cuda_stream)
+        engines.append(e_)
+    eng = engines[0]
+    table_bytes = sum(N * e_.S * e_.T * (8 if e_.A == 6 else e_.A) * real_size for e_ in engines)
 
-    sums_dev = torch.zeros((chunk, 4), dtype=torch.float64, device="cuda")
+    sums_dev = [torch.zeros((chunk, 4), dtype=torch.float64, device="cuda") for _ in cells]
     rec_dtype_size = 16 if real == 0 else 32
     state = {"k": 0}
-    acc = {"train_steps": 0, "eval_steps": 0, "kernel_ms": 0.0, "launches": 0, "trace_rows": 0}
+    acc = {"train_steps": 0, "eval_steps": 0, "kernel_ms": 0.0, "launches": 0, "trace_rows": 0, "alg_bytes": 0}
 
     def step(host_out=None, count=True):
         k = state["k"]
         c = k % chunks_per_run
-        if c == 0 and k > 0:
-            eng.agent_reset()                                   # src/bin/taxi.rs:200
-        if host_out is None:
-            r = eng.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=sums_dev)
-        else:
-            r = eng.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=host_out[0], episodes_out=host_out[1])
-        if world > 1:                                           # the run's one collective: per-episode metrics to rank 0
-            if host_out is not None:
-                sums_dev.copy_(host_out[0], non_blocking=True)
-            state["curves"] = sh.gather_episode_sums(sums_dev)   # [world, chunk, 4] on rank 0
+        for ci, (cell, e_) in enumerate(zip(cells, engines)):
+            if c == 0 and k > 0:
+                e_.agent_reset()                                # src/bin/taxi.rs:200
+            if host_out is None:
+                r = e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=sums_dev[ci])
+            else:
+                r = e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=host_out[0][ci], episodes_out=host_out[1][ci])
+            if world > 1:                                       # the path's one collective: per-episode metrics to rank 0
+                if host_out is not None:
+                    sums_dev[ci].copy_(host_out[0][ci], non_blocking=True)
+                state["curves"] = sh.gather_episode_sums(sums_dev[ci])   # [world, chunk, 4] on rank 0
+            if count:
+                acc["train_steps"] += r["train_steps"]; acc["eval_steps"] += r["eval_steps"]
+                acc["kernel_ms"] += r["kernel_ms"]; acc["launches"] += r["kernel_launches"] + 1   # + k_episode_sums
+                acc["trace_rows"] += r["trace_rows"]
+                acc["alg_bytes"] += algorithmic_bytes(cell, real_size, r["train_steps"], r["trace_rows"])
         state["k"] = k + 1
-        if count:
-            acc["train_steps"] += r["train_steps"]; acc["eval_steps"] += r["eval_steps"]
-            acc["kernel_ms"] += r["kernel_ms"]; acc["launches"] += r["kernel_launches"] + 1   # + k_episode_sums
-            acc["trace_rows"] += r["trace_rows"]
-        return r
 
     def barrier():
         if world > 1:
@@ -308,9 +325,9 @@ def main():
     # ---- e2e leg: same steps, host buffers, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        host_sums = torch.zeros((chunk, 4), dtype=torch.float64).pin_memory()
-        host_eps = torch.zeros((chunk, N, rec_dtype_size // 4), dtype=torch.int32).pin_memory()
-        acc.update(train_steps=0, eval_steps=0, kernel_ms=0.0, launches=0, trace_rows=0)
+        host_sums = [torch.zeros((chunk, 4), dtype=torch.float64).pin_memory() for _ in cells]
+        host_eps = [torch.zeros((chunk, N, rec_dtype_size // 4), dtype=torch.int32).pin_memory() for _ in cells]
+        acc.update(train_steps=0, eval_steps=0, kernel_ms=0.0, launches=0, trace_rows=0, alg_bytes=0)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -320,7 +337,7 @@ def main():
         barrier()
         e2e_ms = e0.elapsed_time(e1)
         e2e = {"ms": e2e_ms, "train_steps": acc["train_steps"],
-               "d2h": chunk * N * rec_dtype_size + chunk * 32 + 64, "h2d": 24}
+               "d2h": len(cells) * (chunk * N * rec_dtype_size + chunk * 32 + 64), "h2d": 24 * len(cells)}
 
     # ---- reduce over ranks: max time, sum of units
     def allreduce(vals, op):
@@ -338,14 +355,14 @@ def main():
         value = train_steps / (ms_max * 1e-3)
         peak, peak_src = peaks()
         # dominant kernel = k_run; per-launch duration measured live by the library (CUDA events on the engine's stream)
-        n_launch = max(1, dev["launches"] - args.steps)          # k_run launches on this rank
-        alg_bytes = algorithmic_bytes(w, real_size, dev["train_steps"], dev["trace_rows"])
+        n_launch = max(1, dev["launches"] // 2)                   # k_run launches on this rank (each followed by one k_episode_sums)
+        alg_bytes = dev["alg_bytes"]
         achieved = alg_bytes / (dev["kernel_ms"] * 1e-3) / 1e9 if dev["kernel_ms"] > 0 else 0.0
         line = {
             "metric": "agent-env steps/sec (updates incl.)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.real, "data": "synthetic",
-            "config": {"workload": args.workload + ": " + w["desc"], "agents_per_gpu": N, "agents_total": N * world,
+            "config": {"workload": args.workload + ": " + w["desc"], "agents_per_gpu": N * len(cells), "agents_total": N * len(cells) * world, "cells": len(cells),
                        "episodes_per_step": chunk, "n_episodes": n_ep, "eval_at": eval_at,
                        "table_store": {1: "hbm", 2: "shared_memory_groups", 3: "hybrid_smem_q_l2_traces"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)],
                        "eval_steps_executed_not_counted": eval_steps, "env_steps_per_s_incl_eval": (train_steps + eval_steps) / (ms_max * 1e-3),
@@ -355,7 +372,7 @@ def main():
             "clocks": clocks,
             "gpu_launches": int(dev["launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_run", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(args.workload, N, args.real), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(args.workload, N, args.real) if len(cells) == 1 else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes / n_launch, "launch_ms": dev["kernel_ms"] / n_launch,
                          "kernel_share_of_step": dev["kernel_ms"] / ms if ms > 0 else None},
         }
@@ -365,13 +382,17 @@ def main():
                            "note": "C-ABI rlb_agent_train_range with pinned HOST buffers: per-agent episode records + per-episode sums copied "
                                    "device->host every step; the path has no per-step host inputs besides the call's scalar arguments"}
         if world == 1 and not args.no_cpu_baseline:
-            cpu_agents = 512   # ~10 s of single-thread CPU work for c2
-            ts, dt, _ = cpu_sample(w, real, cpu_agents, 1, 0, n_ep)
+            cpu_agents = 512 if len(cells) == 1 else 4   # ~10 s of single-thread CPU work
+            ts, dt = 0, 0.0
+            for cell in cells:
+                ts_, dt_, _ = cpu_sample(cell, real, cpu_agents, 1, 0, n_ep)
+                ts += ts_; dt += dt_
             line["cpu_baseline"] = {"value": ts / dt, "unit": "agent-steps/s", "cores": 1, "kind": "port",
-                                    "sample": "%d agents x one full %d-episode run (eval_at %d), C++ oracle single thread, %.1f s"
-                                              % (cpu_agents, n_ep, eval_at, dt)}
+                                    "sample": "%d agents%s x one full %d-episode run (eval_at %d), C++ oracle single thread, %.1f s"
+                                              % (cpu_agents, " per cell" if len(cells) > 1 else "", n_ep, eval_at, dt)}
         print(json.dumps(line), flush=True)
-    eng.close()
+    for e_ in engines:
+        e_.close()
     if world > 1:
         dist.destroy_process_group()
 
