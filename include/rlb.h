@@ -94,7 +94,8 @@ typedef enum rlb_decay_kind { RLB_DECAY_SUB = 0, RLB_DECAY_MUL = 1 } rlb_decay_k
  *             UpperConfidenceBound::new(c) upper_confidence_bound.rs:17
  *   agent:    OneStepAgent::new(policy, gamma, selector, f) one_step_agent.rs:16 |
  *             ElegibilityTracesAgent::new(policy, gamma, selector, lambda, f)
- *             elegibility_traces_agent.rs:21
+ *             elegibility_traces_agent.rs:21 | InternalModelAgent::new(agent, model, planning_length)
+ *             internal_model_agent.rs:17
  * plus the RNG injection contract (seed, global agent ids) and the device placement. */
 typedef struct rlb_config {
     uint32_t struct_size;        /* = sizeof(rlb_config) */
@@ -122,7 +123,8 @@ typedef struct rlb_config {
     uint64_t first_agent_id;     /* global id of local agent 0 (Philox counter high words) */
     uint32_t store_kind;         /* where the fused kernel keeps the tables: 0 = auto, 1 = HBM, 2 = shared memory (one agent per
                                     4-lane thread group), 3 = hybrid (Q in shared memory, eligibility rows streamed through L2) */
-    uint32_t reserved;
+    uint32_t planning_steps;     /* > 0: the agent is wrapped as InternalModelAgent::new(agent, RandomModel::default(), planning_steps)
+                                    (agent/internal_model_agent.rs:17-29; bin/cliffwalking_model.rs:150-156 passes 10).  Needs the HBM store. */
 } rlb_config;
 
 /* Per-training-episode record streamed by the fused kernel (agent.rs:72-75,98,103,115):
@@ -175,6 +177,9 @@ typedef struct rlb_agent_state {
     int32_t env_ready;           /* env `ready` flag */
 } rlb_agent_state;
 
+/* One remembered transition of the Dyna model: `(obs, action) -> (next_obs, reward)` (model/random_model.rs:11). */
+typedef struct rlb_model_entry { uint32_t obs; uint32_t action; uint32_t next_obs; float reward; } rlb_model_entry;
+
 /* ---- library ------------------------------------------------------------------------- */
 int rlb_abi_version(void);
 const char* rlb_last_error_string(void);
@@ -219,7 +224,14 @@ rlb_status rlb_agent_set_action_selector(rlb_engine* e, int32_t selector_kind);
  * engine's agent by a freshly constructed one of `agent_kind`: default tables, policy_flag = true, a fresh selector of
  * the current selector kind, no traces; the env state and the stream position carry on. */
 rlb_status rlb_agent_set_kind(rlb_engine* e, int32_t agent_kind);
-/* Agent::reset (one_step_agent.rs:43-46): selector.reset() + policy.reset() */
+/* InternalModelAgent::new(agent, RandomModel::default(), planning_steps) (agent/internal_model_agent.rs:17-29) around the
+ * engine's CURRENT agent, which keeps its tables and selector state (the wrapper only borrows it); the model starts
+ * empty.  planning_steps = 0 drops the wrapper and its model.  From then on rlb_agent_update and rlb_agent_train run
+ * InternalModelAgent::update (:46-79): the wrapped update, Model::add_info, then `planning_steps` replays of sampled
+ * transitions (get_action on the remembered next_obs + update with terminated = false).  Needs the HBM store. */
+rlb_status rlb_agent_set_model(rlb_engine* e, uint32_t planning_steps);
+/* Agent::reset (one_step_agent.rs:43-46): selector.reset() + policy.reset(); with a model also Model::reset
+ * (internal_model_agent.rs:81-84) */
 rlb_status rlb_agent_reset(rlb_engine* e);
 /* Agent::train (agent.rs:66-118): the fused hot path.  All N agents run episodes
  * [0, n_episodes) with evaluate(100) injected after every episode with
@@ -256,6 +268,20 @@ rlb_status rlb_selector_update(rlb_engine* e);
 /* ActionSelection::reset (uniform_epsilon_greed.rs:78-80, upper_confidence_bound.rs:65-68) */
 rlb_status rlb_selector_reset(rlb_engine* e);
 
+/* ---- Model<T,COUNT> (model.rs:12-16; RandomModel, model/random_model.rs), batched -------------- */
+/* Model::add_info (random_model.rs:37-41): first-seen (obs, action) only, in insertion order.  reward [N] f64 */
+rlb_status rlb_model_add_info(rlb_engine* e, const uint32_t* obs, const uint32_t* action, const double* reward, const uint32_t* next_obs);
+/* Model::get_info (random_model.rs:27-35): entry number gen_range(0..len) of each agent's model, drawn from the agent's
+ * stream.  RLB_ERR_INVALID_ARG if any agent's model is empty (the reference panics); those agents draw nothing. */
+rlb_status rlb_model_get_info(rlb_engine* e, uint32_t* obs_out, uint32_t* action_out, uint32_t* next_obs_out, double* reward_out);
+/* Model::reset (random_model.rs:43-45) */
+rlb_status rlb_model_reset(rlb_engine* e);
+/* entries one agent's model can hold (= S * A); 0 while no model is attached */
+uint32_t rlb_model_capacity(const rlb_engine* e);
+/* snapshot of the models: len [N] u32, entries [N][capacity] in insertion order (host or device buffers) */
+rlb_status rlb_download_model(rlb_engine* e, uint32_t* len_out, rlb_model_entry* entries_out);
+rlb_status rlb_upload_model(rlb_engine* e, const uint32_t* len, const rlb_model_entry* entries);
+
 /* ---- state snapshot (no reference equivalent: the crate has no checkpointing) --------------- */
 /* q: [N][n_tables][S][A] Real (alpha then beta for Double); counts: [N][S][A] u32 (UCB). */
 rlb_status rlb_download_tables(rlb_engine* e, void* q_out, uint32_t* counts_out);
@@ -265,7 +291,7 @@ rlb_status rlb_set_agent_states(rlb_engine* e, const rlb_agent_state* states /* 
 
 /* ---- RNG injection contract, host-callable (no device needed) -------------------------------
  * Replaces rand::thread_rng() at blackjack.rs:54,76; taxi.rs:136-137; frozen_lake.rs:107-108,126;
- * uniform_epsilon_greed.rs:53,62.  Stream of agent g: 32-bit words
+ * uniform_epsilon_greed.rs:53,62; random_model.rs:30.  Stream of agent g: 32-bit words
  * w[n] = Philox4x32-10(key = seed, ctr = (n>>2, g))[n & 3]. */
 void rlb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void rlb_rng_words(uint64_t seed, uint64_t agent_id, uint64_t first_word, uint64_t count, uint32_t* out);
@@ -273,6 +299,8 @@ void rlb_rng_words(uint64_t seed, uint64_t agent_id, uint64_t first_word, uint64
 double rlb_rng_uniform_f64(uint64_t seed, uint64_t agent_id, uint64_t* word_index);
 uint64_t rlb_rng_uniform_usize(uint64_t seed, uint64_t agent_id, uint64_t* word_index, uint64_t range);
 uint32_t rlb_rng_card(uint64_t seed, uint64_t agent_id, uint64_t* word_index);
+/* `Rng::gen_range(0..range)` on usize (the one-shot sampler with the conservative zone, random_model.rs:30) */
+uint64_t rlb_rng_gen_range(uint64_t seed, uint64_t agent_id, uint64_t* word_index, uint64_t range);
 
 /* ---- Blackjack observation ids (blackjack.rs:10-28) ------------------------------------------ */
 uint64_t rlb_blackjack_obs_id(uint32_t dense_index);

@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -99,6 +100,20 @@ inline double uniform_f64(Stream& rng) {
 inline u64 uniform_usize(Stream& rng, u64 range) {
     const u64 ints_to_reject = (UINT64_MAX - range + 1) % range;
     const u64 zone = UINT64_MAX - ints_to_reject;
+    for (;;) {
+        u64 v = rng.next_u64();
+        unsigned __int128 m = (unsigned __int128)v * range;
+        u64 hi = (u64)(m >> 64), lo = (u64)m;
+        if (lo <= zone) return hi;
+    }
+}
+
+// rand 0.8.5 `Rng::gen_range(0..range)` on usize (64-bit target) = `UniformInt<usize>::sample_single_inclusive(0,
+// range-1)`: the same widening multiply, but the one-shot path skips the modulus and uses the conservative zone
+// `(range << range.leading_zeros()) - 1` (rejects up to half of the draws; a 1-entry range still rejects v >= 2^63).
+// Call site: model/random_model.rs:30.
+inline u64 gen_range_usize(Stream& rng, u64 range) {
+    const u64 zone = (range << __builtin_clzll(range)) - 1;
     for (;;) {
         u64 v = rng.next_u64();
         unsigned __int128 m = (unsigned __int128)v * range;
@@ -908,6 +923,50 @@ struct ElegibilityTracesAgent : Agent<A, Real> {
         if (terminated) { trace.clear(); action_selection->update(); }
         return temporal_difference;
     }
+};
+
+// model/random_model.rs:9-45 — `IndexMap<(T, usize), (T, f64)>`: first-seen transitions in insertion order
+// (nothing is ever removed, so `get_index(i)` is the i-th inserted entry).
+template <int A, class Real>
+struct RandomModel {
+    struct Info { u64 obs; size_t action; u64 next_obs; Real reward; };
+    std::vector<Info> values;
+    std::map<std::pair<u64, size_t>, size_t> slot;   // key -> index into `values`
+    Stream* rng;
+    explicit RandomModel(Stream* rng_) : rng(rng_) {}
+    Info get_info() { return values[(size_t)gen_range_usize(*rng, (u64)values.size())]; }                       // :27-35 (panics when empty)
+    void add_info(u64 obs, size_t action, Real reward, u64 next_obs) {                                            // :37-41 `.entry().or_insert()`
+        auto key = std::make_pair(obs, action);
+        if (slot.find(key) != slot.end()) return;
+        slot.emplace(key, values.size());
+        values.push_back({obs, action, next_obs, reward});
+    }
+    void reset() { values.clear(); slot.clear(); }                                                                // :43-45
+};
+
+// agent/internal_model_agent.rs:9-85 — Dyna: wraps a borrowed agent, learns a model of the transitions it sees and
+// replays `planning_steps` sampled ones after every real update.
+template <int A, class Real>
+struct InternalModelAgent : Agent<A, Real> {
+    Agent<A, Real>* agent;   // `Box<RefCell<&'a mut dyn Agent>>`
+    RandomModel<A, Real> model;
+    size_t planning_steps;
+    InternalModelAgent(Agent<A, Real>* inner, RandomModel<A, Real> m, size_t planning_length)
+        : agent(inner), model(std::move(m)), planning_steps(planning_length) {}
+    void set_future_q_value_func(GetNextQValue<A, Real> f) override { agent->set_future_q_value_func(f); }                       // :34-36
+    void set_action_selector(std::unique_ptr<ActionSelection<A, Real>> s) override { agent->set_action_selector(std::move(s)); }   // :38-40
+    size_t get_action(u64 obs) override { return agent->get_action(obs); }                                                       // :42-44
+    Real update(u64 curr_obs, size_t curr_action, Real reward, bool terminated, u64 next_obs, size_t next_action) override {     // :46-79
+        Real td = agent->update(curr_obs, curr_action, reward, terminated, next_obs, next_action);
+        model.add_info(curr_obs, curr_action, reward, next_obs);
+        for (size_t i = 0; i < planning_steps; ++i) {
+            auto info = model.get_info();
+            size_t planned_action = agent->get_action(info.next_obs);
+            agent->update(info.obs, info.action, info.reward, false, info.next_obs, planned_action);
+        }
+        return td;
+    }
+    void reset() override { agent->reset(); model.reset(); }                                                                     // :81-84
 };
 
 }   // namespace oracle

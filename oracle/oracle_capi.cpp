@@ -26,6 +26,8 @@ struct OracleConfig {
     int32_t decay_kind;      // 0 eps - param, 1 eps * param
     double lr, gamma, lambda, eps0, eps_decay, eps_final, ucb_c, default_q;
     uint64_t seed;
+    uint32_t planning_steps; // > 0: the agent is wrapped in InternalModelAgent(RandomModel, planning_steps)
+    uint32_t pad;
 };
 
 struct OracleState {
@@ -58,6 +60,12 @@ struct SessionBase {
     virtual u32 get_action(u32 dense_obs) = 0;
     virtual double update(u32 s, u32 a, double r, int term, u32 s2, u32 a2) = 0;
     virtual void record(bool on) = 0;
+    virtual void set_planning(u32 steps) = 0;
+    virtual u64 model_len() = 0;
+    virtual void model_copy(u32* s, u32* a, u32* s2, double* r) = 0;
+    virtual void model_add_info(u32 s, u32 a, double r, u32 s2) = 0;
+    virtual int model_get_info(u32* s, u32* a, u32* s2, double* r) = 0;
+    virtual void model_reset() = 0;
     std::vector<TrajRecord> traj;
     std::vector<double> training_error;   // widened copy of the last train() call's per-step TD
     u64 train_steps = 0;
@@ -68,7 +76,9 @@ struct Session : SessionBase {
     OracleConfig cfg;
     Stream rng;
     std::unique_ptr<Env<A>> env;
+    std::unique_ptr<Agent<A, Real>> inner;            // the wrapped agent when a model is attached
     std::unique_ptr<Agent<A, Real>> agent;
+    InternalModelAgent<A, Real>* dyna = nullptr;
     Policy<A, Real>* policy_raw = nullptr;            // borrowed views for export
     TabularPolicy<A, Real>* basic = nullptr;
     DoubleTabularPolicy<A, Real>* dbl = nullptr;
@@ -114,7 +124,43 @@ struct Session : SessionBase {
         else
             agent.reset(new ElegibilityTracesAgent<A, Real>(std::move(pol), (Real)cfg.gamma, std::move(sel),
                                                             (Real)cfg.lambda, target_fn(cfg.target_kind)));
+        dyna = nullptr;
+        inner.reset();
+        if (cfg.planning_steps) wrap_with_model();
     }
+    // InternalModelAgent::new(Box::new(RefCell::new(&mut other)), EnumModel::from(RandomModel::default()), n)
+    // (bin/cliffwalking_model.rs:150-156): the wrapped agent keeps its tables.
+    void wrap_with_model() {
+        inner = std::move(agent);
+        dyna = new InternalModelAgent<A, Real>(inner.get(), RandomModel<A, Real>(&rng), cfg.planning_steps);
+        agent.reset(dyna);
+    }
+    void set_planning(u32 steps) override {
+        std::vector<TrajRecord>* tap = agent->recorder;
+        u64 ev = agent->eval_steps;
+        if (dyna) { agent = std::move(inner); dyna = nullptr; }   // unwrap (drops the model)
+        cfg.planning_steps = steps;
+        if (steps) wrap_with_model();
+        agent->recorder = tap;
+        agent->eval_steps = ev;
+    }
+    u64 model_len() override { return dyna ? dyna->model.values.size() : 0; }
+    void model_copy(u32* s, u32* a, u32* s2, double* r) override {
+        if (!dyna) return;
+        size_t i = 0;
+        for (auto& v : dyna->model.values) {
+            s[i] = env->dense_index(v.obs); a[i] = (u32)v.action; s2[i] = env->dense_index(v.next_obs); r[i] = (double)v.reward;
+            ++i;
+        }
+    }
+    void model_add_info(u32 s, u32 a, double r, u32 s2) override { if (dyna) dyna->model.add_info(id_of_dense[s], a, (Real)r, id_of_dense[s2]); }
+    int model_get_info(u32* s, u32* a, u32* s2, double* r) override {
+        if (!dyna || dyna->model.values.empty()) return 1;   // the reference panics on an empty range
+        auto v = dyna->model.get_info();
+        *s = env->dense_index(v.obs); *a = (u32)v.action; *s2 = env->dense_index(v.next_obs); *r = (double)v.reward;
+        return 0;
+    }
+    void model_reset() override { if (dyna) dyna->model.reset(); }
     int train(u64 ep_begin, u64 ep_end, u64 eval_at, double* ret, u64* len, double* tdsum, double* tdabs) override {
         std::vector<Real> r, te; std::vector<u64> l;
         if (eval_at == 0) return 2;   // reference: division by zero panic (agent.rs:107)
@@ -272,6 +318,14 @@ double oracle_update(void* h, uint32_t s, uint32_t a, double r, int term, uint32
     return ((SessionBase*)h)->update(s, a, r, term, s2, a2);
 }
 
+// Model<T,COUNT> (model.rs:12-16) of the attached RandomModel, and (un)wrapping the agent
+void oracle_set_planning(void* h, uint32_t steps) { ((SessionBase*)h)->set_planning(steps); }
+uint64_t oracle_model_len(void* h) { return ((SessionBase*)h)->model_len(); }
+void oracle_model_copy(void* h, uint32_t* s, uint32_t* a, uint32_t* s2, double* r) { ((SessionBase*)h)->model_copy(s, a, s2, r); }
+void oracle_model_add_info(void* h, uint32_t s, uint32_t a, double r, uint32_t s2) { ((SessionBase*)h)->model_add_info(s, a, r, s2); }
+int oracle_model_get_info(void* h, uint32_t* s, uint32_t* a, uint32_t* s2, double* r) { return ((SessionBase*)h)->model_get_info(s, a, s2, r); }
+void oracle_model_reset(void* h) { ((SessionBase*)h)->model_reset(); }
+
 // ------------------------------------------------------------------ batch runner
 // Runs agents [first_agent, first_agent+count): create, train [0,n_episodes) with eval_at,
 // export.  Any output pointer may be null.  Layouts: ret/len/tdsum/tdabs [count][n_episodes];
@@ -326,12 +380,13 @@ void oracle_stream_words(uint64_t seed, uint64_t agent, uint64_t start_n, uint64
     for (u64 i = 0; i < count; ++i) out[i] = s.next_u32();
 }
 // draws `count` values of one sampler kind from the stream starting at word start_n:
-// kind 0 uniform_f64 (out as double), 1 uniform_usize(range), 2 card.  Returns words consumed.
+// kind 0 uniform_f64 (out as double), 1 uniform_usize(range), 2 card, 3 gen_range(0..range).  Returns words consumed.
 uint64_t oracle_sample(uint64_t seed, uint64_t agent, uint64_t start_n, int kind, uint64_t range, uint64_t count, double* out) {
     Stream s(seed, agent, start_n);
     for (u64 i = 0; i < count; ++i) {
         if (kind == 0) out[i] = uniform_f64(s);
         else if (kind == 1) out[i] = (double)uniform_usize(s, range);
+        else if (kind == 3) out[i] = (double)gen_range_usize(s, range);
         else out[i] = (double)uniform_card(s);
     }
     return s.n - start_n;

@@ -28,7 +28,7 @@ class OracleConfig(C.Structure):
         ("agent_kind", C.c_int32), ("real_kind", C.c_int32), ("decay_kind", C.c_int32),
         ("lr", C.c_double), ("gamma", C.c_double), ("lambda_", C.c_double), ("eps0", C.c_double),
         ("eps_decay", C.c_double), ("eps_final", C.c_double), ("ucb_c", C.c_double), ("default_q", C.c_double),
-        ("seed", C.c_uint64),
+        ("seed", C.c_uint64), ("planning_steps", C.c_uint32), ("pad", C.c_uint32),
     ]
 
 
@@ -90,6 +90,14 @@ def lib():
         L.oracle_get_action.argtypes = [vp, u32]
         L.oracle_update.restype = dbl
         L.oracle_update.argtypes = [vp, u32, u32, dbl, i32, u32, u32]
+        L.oracle_set_planning.argtypes = [vp, u32]
+        L.oracle_model_len.restype = u64
+        L.oracle_model_len.argtypes = [vp]
+        L.oracle_model_copy.argtypes = [vp, vp, vp, vp, vp]
+        L.oracle_model_add_info.argtypes = [vp, u32, u32, dbl, u32]
+        L.oracle_model_get_info.restype = i32
+        L.oracle_model_get_info.argtypes = [vp, P(u32), P(u32), P(u32), P(dbl)]
+        L.oracle_model_reset.argtypes = [vp]
         L.oracle_batch_train.restype = i32
         L.oracle_batch_train.argtypes = [P(OracleConfig), u64, u64, u64, u64, i32, vp, vp, vp, vp, vp, vp, vp,
                                          P(dbl), P(u64), P(u64)]
@@ -130,10 +138,11 @@ def env_dims(cfg):
 def make_config(env_kind, *, map_id=1, slippery=0, max_steps=100, policy=POLICY_BASIC, selector=SEL_EPS_GREEDY,
                 target=TARGET_QLEARNING, agent=AGENT_ONE_STEP, real=REAL_F64, decay_kind=DECAY_SUB, lr=0.05,
                 gamma=0.95, lambda_=0.5, eps0=1.0, eps_decay=2e-5, eps_final=0.0, ucb_c=0.5, default_q=0.0,
-                seed=0x5EED0001):
+                seed=0x5EED0001, planning_steps=0):
     """Defaults = the reference CLI's (bin/taxi.rs:22-68) with n_episodes=100000 -> decay 2e-5."""
     return OracleConfig(env_kind, map_id, int(slippery), max_steps, policy, selector, target, agent, real,
-                        decay_kind, lr, gamma, lambda_, eps0, eps_decay, eps_final, ucb_c, default_q, seed)
+                        decay_kind, lr, gamma, lambda_, eps0, eps_decay, eps_final, ucb_c, default_q, seed,
+                        planning_steps, 0)
 
 
 class Session:
@@ -226,6 +235,31 @@ class Session:
 
     def update(self, s, a, r, term, s2, a2):
         return self.L.oracle_update(self.h, s, a, r, int(term), s2, a2)
+
+    # InternalModelAgent / RandomModel (agent/internal_model_agent.rs, model/random_model.rs)
+    def set_planning(self, steps):
+        self.L.oracle_set_planning(self.h, steps)
+
+    def model(self):
+        """The model's entries in insertion order: arrays (obs, action, next_obs, reward)."""
+        n = self.L.oracle_model_len(self.h)
+        s, a, s2 = (np.zeros(n, np.uint32) for _ in range(3))
+        r = np.zeros(n, np.float64)
+        if n:
+            self.L.oracle_model_copy(self.h, _p(s), _p(a), _p(s2), _p(r))
+        return s, a, s2, r
+
+    def model_add_info(self, s, a, r, s2):
+        self.L.oracle_model_add_info(self.h, s, a, r, s2)
+
+    def model_get_info(self):
+        s, a, s2, r = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_double()
+        if self.L.oracle_model_get_info(self.h, C.byref(s), C.byref(a), C.byref(s2), C.byref(r)):
+            return None
+        return s.value, a.value, s2.value, r.value
+
+    def model_reset(self):
+        self.L.oracle_model_reset(self.h)
 
 
 def batch_train(cfg, first_agent, count, n_episodes, eval_at, n_threads=1, want_tables=True, want_stats=True):

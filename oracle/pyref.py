@@ -53,6 +53,13 @@ class Stream:
             if (m & M64) <= zone:
                 return m >> 64
 
+    def gen_range(self, rng):           # rand 0.8.5 Rng::gen_range(0..rng) on usize: sample_single's cheap zone
+        zone = ((rng << (64 - rng.bit_length())) - 1) & M64
+        while True:
+            m = self.u64() * rng
+            if (m & M64) <= zone:
+                return m >> 64
+
     def card(self):                     # rand 0.8.5 Uniform<u8>(1..11), via u32
         while True:
             m = self.u32() * 10
@@ -530,17 +537,44 @@ class Agent:
         return rewards, lengths
 
 
+class DynaAgent(Agent):                 # agent/internal_model_agent.rs around model/random_model.rs
+    """Wraps `inner`: every real update is followed by add_info and `planning` replays of remembered transitions."""
+
+    def __init__(self, inner, planning, rng):
+        self.inner, self.planning, self.rng = inner, planning, rng
+        self.model = {}                 # IndexMap: python dicts keep insertion order too
+        self.eval_steps = 0
+
+    def get_action(self, o):
+        return self.inner.get_action(o)
+
+    def update(self, s, a, r, term, s2, a2):          # internal_model_agent.rs:46-79
+        td = self.inner.update(s, a, r, term, s2, a2)
+        self.model.setdefault((s, a), (s2, r))        # random_model.rs:37-41
+        for _ in range(self.planning):
+            (ms, ma), (ms2, mr) = list(self.model.items())[self.rng.gen_range(len(self.model))]   # :27-35
+            self.inner.update(ms, ma, mr, False, ms2, self.inner.get_action(ms2))
+        return td
+
+    def reset(self):                                  # :81-84
+        self.inner.reset()
+        self.model = {}
+
+
 def _key(obs):
     return obs[0] if isinstance(obs, tuple) else obs
 
 
 def build(env_kind, *, agent_id=0, seed=0x5EED0001, map_id=1, slippery=True, max_steps=100, policy=0, selector=0, target=1,
           traces=False, lr=0.05, gamma=0.95, lam=0.5, eps0=1.0, eps_decay=2e-5, eps_final=0.0, decay_kind=0, ucb_c=0.5,
-          default_q=0.0):
+          default_q=0.0, planning=0):
     rng = Stream(seed, agent_id)
     env = {0: lambda: BlackJack(rng), 1: lambda: FrozenLake(map_id, slippery, max_steps, rng),
            2: lambda: CliffWalking(max_steps), 3: lambda: Taxi(max_steps, rng)}[env_kind]()
     count = env.COUNT
     pol = (DoubleTabular if policy else Tabular)(lr, default_q, count)
     sel = UCB(ucb_c, count) if selector else EpsGreedy(eps0, decay_kind, eps_decay, eps_final, count, rng)
-    return env, Agent(pol, gamma, sel, target, traces, lam), rng
+    agent = Agent(pol, gamma, sel, target, traces, lam)
+    if planning:
+        agent = DynaAgent(agent, planning, rng)
+    return env, agent, rng

@@ -33,7 +33,7 @@ class RlbConfig(C.Structure):
         ("initial_epsilon", C.c_double), ("epsilon_decay", C.c_double), ("final_epsilon", C.c_double),
         ("confidence_level", C.c_double), ("default_value", C.c_double),
         ("seed", C.c_uint64), ("n_agents", C.c_uint64), ("first_agent_id", C.c_uint64),
-        ("store_kind", C.c_uint32), ("reserved", C.c_uint32),
+        ("store_kind", C.c_uint32), ("planning_steps", C.c_uint32),
     ]
 
 
@@ -52,18 +52,20 @@ TRAJ_DTYPE = np.dtype([("kind", "u1"), ("action", "u1"), ("terminated", "u1"), (
                        ("reward", "<f8"), ("td", "<f8")])
 STATE_DTYPE = np.dtype([("epsilon", "<f8"), ("ucb_t", "<u8"), ("rng_n", "<u8"), ("policy_flag", "<i4"),
                         ("env_ready", "<i4")])
+MODEL_ENTRY = np.dtype([("obs", "<u4"), ("action", "<u4"), ("next_obs", "<u4"), ("reward", "<f4")])
 
 # every symbol include/rlb.h declares
 EXPORTS = [
     "rlb_abi_version", "rlb_last_error_string", "rlb_device_count", "rlb_engine_create", "rlb_engine_destroy",
     "rlb_engine_set_stream", "rlb_engine_synchronize", "rlb_engine_dims", "rlb_engine_store_kind", "rlb_env_reset",
     "rlb_env_step", "rlb_agent_get_action", "rlb_agent_update", "rlb_agent_set_future_q_value_func",
-    "rlb_agent_set_action_selector", "rlb_agent_set_kind", "rlb_agent_reset", "rlb_agent_train", "rlb_agent_train_range",
+    "rlb_agent_set_action_selector", "rlb_agent_set_kind", "rlb_agent_set_model", "rlb_agent_reset", "rlb_agent_train", "rlb_agent_train_range",
     "rlb_agent_evaluate", "rlb_policy_predict", "rlb_policy_get_values", "rlb_policy_update",
     "rlb_policy_after_update", "rlb_policy_reset", "rlb_selector_get_action", "rlb_selector_get_exploration_probs",
     "rlb_selector_update", "rlb_selector_reset", "rlb_download_tables", "rlb_upload_tables", "rlb_get_agent_states",
     "rlb_set_agent_states", "rlb_philox4x32_10", "rlb_rng_words", "rlb_rng_uniform_f64", "rlb_rng_uniform_usize",
-    "rlb_rng_card", "rlb_blackjack_obs_id", "rlb_blackjack_dense_index", "rlb_blackjack_decode",
+    "rlb_rng_card", "rlb_rng_gen_range", "rlb_model_add_info", "rlb_model_get_info", "rlb_model_reset", "rlb_model_capacity",
+    "rlb_download_model", "rlb_upload_model", "rlb_blackjack_obs_id", "rlb_blackjack_dense_index", "rlb_blackjack_decode",
 ]
 
 
@@ -105,6 +107,16 @@ def _load():
     L.rlb_agent_set_action_selector.argtypes = [vp, i32]
     L.rlb_agent_set_kind.argtypes = [vp, i32]
     L.rlb_agent_reset.argtypes = [vp]
+    L.rlb_agent_set_model.argtypes = [vp, u32]
+    L.rlb_model_add_info.argtypes = [vp, vp, vp, vp, vp]
+    L.rlb_model_get_info.argtypes = [vp, vp, vp, vp, vp]
+    L.rlb_model_reset.argtypes = [vp]
+    L.rlb_model_capacity.restype = u32
+    L.rlb_model_capacity.argtypes = [vp]
+    L.rlb_download_model.argtypes = [vp, vp, vp]
+    L.rlb_upload_model.argtypes = [vp, vp, vp]
+    L.rlb_rng_gen_range.restype = u64
+    L.rlb_rng_gen_range.argtypes = [u64, u64, P(u64), u64]
     L.rlb_agent_train.argtypes = [vp, u64, u64, P(RlbTrainOut)]
     L.rlb_agent_train_range.argtypes = [vp, u64, u64, u64, P(RlbTrainOut)]
     L.rlb_agent_evaluate.argtypes = [vp, u64, vp, vp, P(u64)]
@@ -174,11 +186,11 @@ class Engine:
                  selector=SEL_EPS_GREEDY, target=TARGET_QLEARNING, agent=AGENT_ONE_STEP, real=REAL_F32,
                  decay_kind=DECAY_SUB, learning_rate=0.05, discount_factor=0.95, lambda_factor=0.5,
                  initial_epsilon=1.0, epsilon_decay=2e-5, final_epsilon=0.0, confidence_level=0.5, default_value=0.0,
-                 seed=0x5EED0001, first_agent_id=0, device=0, store_kind=0):
+                 seed=0x5EED0001, first_agent_id=0, device=0, store_kind=0, planning_steps=0):
         self.cfg = RlbConfig(C.sizeof(RlbConfig), env_kind, map_id, int(bool(slippery)), max_steps, policy, selector,
                              target, agent, real, decay_kind, device, learning_rate, discount_factor, lambda_factor,
                              initial_epsilon, epsilon_decay, final_epsilon, confidence_level, default_value, seed,
-                             n_agents, first_agent_id, store_kind, 0)
+                             n_agents, first_agent_id, store_kind, planning_steps)
         self.h = C.c_void_p()
         check(lib.rlb_engine_create(C.byref(self.cfg), C.byref(self.h)))
         s, a, t = C.c_uint32(), C.c_uint32(), C.c_uint32()
@@ -208,6 +220,10 @@ class Engine:
 
     def synchronize(self):
         check(lib.rlb_engine_synchronize(self.h))
+
+    def store_kind(self):
+        """Which table store the fused kernel runs with: 1 HBM, 2 shared-memory thread groups, 3 hybrid."""
+        return lib.rlb_engine_store_kind(self.h)
 
     # ---- Agent::train / evaluate
     def train(self, n_episodes, eval_at, *, ep_begin=0, sums=True, episodes=False, traj_capacity=0, sums_out=None,
@@ -264,6 +280,38 @@ class Engine:
 
     def agent_reset(self):
         check(lib.rlb_agent_reset(self.h))
+
+    # ---- InternalModelAgent / Model (agent/internal_model_agent.rs, model/random_model.rs)
+    def set_model(self, planning_steps):
+        check(lib.rlb_agent_set_model(self.h, planning_steps))
+        self.cfg.planning_steps = planning_steps
+
+    def model_add_info(self, obs, action, reward, next_obs):
+        obs, action, next_obs = (np.ascontiguousarray(x, np.uint32) for x in (obs, action, next_obs))
+        reward = np.ascontiguousarray(reward, np.float64)
+        check(lib.rlb_model_add_info(self.h, ptr(obs), ptr(action), ptr(reward), ptr(next_obs)))
+
+    def model_get_info(self):
+        obs, action, next_obs = (np.zeros(self.N, np.uint32) for _ in range(3))
+        reward = np.zeros(self.N, np.float64)
+        check(lib.rlb_model_get_info(self.h, ptr(obs), ptr(action), ptr(next_obs), ptr(reward)))
+        return obs, action, next_obs, reward
+
+    def model_reset(self):
+        check(lib.rlb_model_reset(self.h))
+
+    def download_model(self):
+        """(len [N], entries [N][capacity]) — each agent's remembered transitions in insertion order."""
+        cap = lib.rlb_model_capacity(self.h)
+        ln = np.zeros(self.N, np.uint32)
+        ent = np.zeros((self.N, cap), MODEL_ENTRY)
+        check(lib.rlb_download_model(self.h, ptr(ln), ptr(ent)))
+        return ln, ent
+
+    def upload_model(self, ln, ent):
+        ln = np.ascontiguousarray(ln, np.uint32)
+        ent = np.ascontiguousarray(ent, MODEL_ENTRY)
+        check(lib.rlb_upload_model(self.h, ptr(ln), ptr(ent)))
 
     # ---- snapshots
     def download_tables(self, counts=True):

@@ -70,6 +70,9 @@ struct rlb_engine {
     uint16_t* d_trans = nullptr;
     uint64_t* d_thr = nullptr;
     uint16_t* d_thr_state = nullptr;
+    uint2* d_model_ent = nullptr;       // Dyna model (only while an InternalModelAgent wraps the agent)
+    uint32_t* d_model_bits = nullptr;
+    uint32_t* d_model_len = nullptr;
     unsigned long long* d_totals = nullptr;   // [8]: train steps, eval steps, eval episodes, (double) eval return, trace rows
     uint32_t* d_flagword = nullptr;
     // scratch
@@ -146,6 +149,14 @@ cudaError_t fill_q_default(rlb_engine* e) {
 }
 
 cudaError_t dispatch_run(rlb_engine* e, const DevParams& p) {
+    if (p.planning_steps && p.mode == 0) {   // InternalModelAgent::update on the training path; evaluate never touches the model
+        switch (e->cfg.env_kind) {
+            case RLB_ENV_BLACKJACK: return launch_run_model<RLB_ENV_BLACKJACK>(e->variant, p, e->stream);
+            case RLB_ENV_FROZEN_LAKE: return launch_run_model<RLB_ENV_FROZEN_LAKE>(e->variant, p, e->stream);
+            case RLB_ENV_CLIFF_WALKING: return launch_run_model<RLB_ENV_CLIFF_WALKING>(e->variant, p, e->stream);
+            default: return launch_run_model<RLB_ENV_TAXI>(e->variant, p, e->stream);
+        }
+    }
     switch (e->cfg.env_kind) {
         case RLB_ENV_BLACKJACK: return launch_run<RLB_ENV_BLACKJACK>(e->variant, p, e->store, e->stream);
         case RLB_ENV_FROZEN_LAKE: return launch_run<RLB_ENV_FROZEN_LAKE>(e->variant, p, e->store, e->stream);
@@ -172,7 +183,11 @@ rlb_status pick_store(rlb_engine* e) {
     const bool fits_group = b_group > 0 && b_group <= per_block_max;
     const bool fits_hybrid = b_hybrid > 0 && b_hybrid <= per_block_max;
     int want = e->cfg.store_kind;
-    if (want == 0) {
+    if (e->cfg.planning_steps) {
+        // planning replays arbitrary remembered states, terminal ones included, and the model itself lives in HBM
+        if (want != 0 && want != STORE_GLOBAL) { set_error("a Dyna model (planning_steps > 0) needs the HBM store"); return RLB_ERR_UNSUPPORTED; }
+        want = STORE_GLOBAL;
+    } else if (want == 0) {
         // measured: one-step updates touch two rows per step and run fastest from HBM at full occupancy;
         // trace sweeps want the tables on chip.  Hybrid when >= 3 warps per SM fit, else the thread-group store (>= 4).
         want = STORE_GLOBAL;
@@ -204,6 +219,64 @@ cudaError_t dispatch_step(rlb_engine* e, StepOp op, const StepArgs& a) {
         case RLB_ENV_CLIFF_WALKING: return launch_step<RLB_ENV_CLIFF_WALKING>(op, e->variant, e->dp, a, e->stream);
         default: return launch_step<RLB_ENV_TAXI>(op, e->variant, e->dp, a, e->stream);
     }
+}
+
+// Eligibility rows an agent can hold.  Without a model: distinct states updated in one episode <= episode length <=
+// max_steps + 1 (truncation pseudo-step), <= S; Blackjack has no step limit, a hand holds at most 16 cards
+// (blackjack.rs:32-35).  With a Dyna model the planning updates (terminated = false, internal_model_agent.rs:68-75) put
+// any remembered state into the trace map and nothing clears it before the next real termination: S rows.
+uint32_t wanted_vmax(const rlb_engine* e) {
+    if (e->cfg.planning_steps) return e->S;
+    const uint64_t by_steps = e->cfg.env_kind == RLB_ENV_BLACKJACK ? 32ull : (uint64_t)e->cfg.max_steps + 1ull;
+    return (uint32_t)std::min<uint64_t>(e->S, by_steps);
+}
+rlb_status ensure_trace_buffers(rlb_engine* e) {
+    if (!e->variant.trace) return RLB_OK;
+    const uint64_t N = e->cfg.n_agents;
+    const uint32_t need = wanted_vmax(e);
+    if (e->d_etr && e->dp.vmax >= need) return RLB_OK;
+    void* etr = nullptr;
+    uint16_t* vis = nullptr;
+    const size_t row = (size_t)e->APAD * e->real_size;
+    CK(cudaMalloc(&etr, (size_t)N * need * row));
+    CK(cudaMalloc(&vis, (size_t)N * need * sizeof(uint16_t)));
+    if (e->d_etr) {   // keep the live rows: same per-agent order, wider stride
+        const size_t old_v = e->dp.vmax;
+        CK(cudaMemcpy2DAsync(etr, need * row, e->d_etr, old_v * row, old_v * row, N, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpy2DAsync(vis, need * 2, e->d_vis, old_v * 2, old_v * 2, N, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_etr); cudaFree(e->d_vis);
+        if (e->d_etr_il) { cudaFree(e->d_etr_il); e->d_etr_il = nullptr; e->dp.etr_il = nullptr; }
+    }
+    e->d_etr = etr; e->d_vis = vis;
+    e->dp.etr = etr; e->dp.vis = vis; e->dp.vmax = need;
+    return RLB_OK;
+}
+
+// InternalModelAgent::new(agent, RandomModel::default(), planning_steps) / unwrap when planning_steps == 0
+rlb_status attach_model(rlb_engine* e, uint32_t planning_steps) {
+    const uint64_t N = e->cfg.n_agents;
+    e->cfg.planning_steps = planning_steps;
+    e->dp.planning_steps = planning_steps;
+    if (!planning_steps) {
+        void* bufs[] = {e->d_model_ent, e->d_model_bits, e->d_model_len};
+        CK(cudaStreamSynchronize(e->stream));
+        for (void* b : bufs) if (b) cudaFree(b);
+        e->d_model_ent = nullptr; e->d_model_bits = nullptr; e->d_model_len = nullptr;
+        e->dp.model_ent = nullptr; e->dp.model_bits = nullptr; e->dp.model_len = nullptr; e->dp.mcap = 0; e->dp.mwords = 0;
+        return RLB_OK;
+    }
+    const uint32_t mcap = e->S * e->A, mwords = (mcap + 31u) / 32u;
+    if (!e->d_model_ent) {
+        CK(cudaMalloc(&e->d_model_ent, (size_t)N * mcap * sizeof(uint2)));
+        CK(cudaMalloc(&e->d_model_bits, (size_t)N * mwords * sizeof(uint32_t)));
+        CK(cudaMalloc(&e->d_model_len, N * sizeof(uint32_t)));
+    }
+    CK(cudaMemsetAsync(e->d_model_bits, 0, (size_t)N * mwords * sizeof(uint32_t), e->stream));
+    CK(cudaMemsetAsync(e->d_model_len, 0, N * sizeof(uint32_t), e->stream));
+    e->dp.model_ent = e->d_model_ent; e->dp.model_bits = e->d_model_bits; e->dp.model_len = e->d_model_len;
+    e->dp.mcap = mcap; e->dp.mwords = mwords;
+    return ensure_trace_buffers(e);
 }
 
 // (re)build the selector state: UniformEpsilonGreed::new / UpperConfidenceBound::new
@@ -325,15 +398,6 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
 
     e->q_bytes = (size_t)N * e->S * e->T * e->APAD * e->real_size;
     CKE(cudaMalloc(&e->d_q, e->q_bytes));
-    uint32_t vmax = 0;
-    if (e->variant.trace) {
-        // distinct states updated in one episode: <= episode length <= max_steps + 1 (truncation pseudo-step), <= S.
-        // Blackjack has no step limit; a hand holds at most 16 cards (blackjack.rs:32-35).
-        uint64_t by_steps = cfg->env_kind == RLB_ENV_BLACKJACK ? 32ull : (uint64_t)cfg->max_steps + 1ull;
-        vmax = (uint32_t)std::min<uint64_t>(e->S, by_steps);
-        CKE(cudaMalloc(&e->d_etr, (size_t)N * vmax * e->APAD * e->real_size));
-        CKE(cudaMalloc(&e->d_vis, (size_t)N * vmax * sizeof(uint16_t)));
-    }
     CKE(cudaMalloc(&e->d_nvis, N * sizeof(uint32_t)));
     CKE(cudaMalloc(&e->d_rng_n, N * sizeof(uint64_t)));
     CKE(cudaMalloc(&e->d_eps, N * sizeof(double)));
@@ -362,19 +426,22 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     p.eps0 = cfg->initial_epsilon; p.eps_decay = cfg->epsilon_decay; p.eps_final = cfg->final_epsilon;
     p.ucb_c = cfg->confidence_level; p.default_q = cfg->default_value;
     p.decay_kind = cfg->decay_kind; p.target = cfg->target_kind;
-    p.max_steps = cfg->max_steps; p.S = e->S; p.vmax = vmax;
+    p.max_steps = cfg->max_steps; p.S = e->S; p.vmax = 0;
     p.n_live = e->tables.n_live;
     std::memcpy(p.row_lut, e->tables.row_lut, sizeof p.row_lut);
     p.seed = cfg->seed; p.first_agent = cfg->first_agent_id; p.n_agents = N;
     p.mode = 0; p.eval_episodes = 100; p.ep0 = p.ep1 = 0; p.eval_at = 1; p.n_eval = 0;
     p.episodes = nullptr; p.traj = nullptr; p.traj_cap = 0; p.traj_count = nullptr;
     p.totals = e->d_totals; p.eval_ret_total = reinterpret_cast<double*>(e->d_totals + 3);
+    p.model_ent = nullptr; p.model_bits = nullptr; p.model_len = nullptr; p.planning_steps = 0; p.mcap = 0; p.mwords = 0;
 
     CKE(fill_q_default(e));
     CKE(cudaMemsetAsync(e->d_nvis, 0, N * sizeof(uint32_t), e->stream));
     CKE(cudaMemsetAsync(e->d_rng_n, 0, N * sizeof(uint64_t), e->stream));
     CKE(fill<uint8_t>(e, e->d_flag, N, (uint8_t)1));   // policy_flag: true (double_tabular_policy.rs:23)
     rlb_status st = install_selector(e, cfg->selector_kind);
+    if (st != RLB_OK) return fail(st);
+    st = cfg->planning_steps ? attach_model(e, cfg->planning_steps) : ensure_trace_buffers(e);
     if (st != RLB_OK) return fail(st);
     st = pick_store(e);
     if (st != RLB_OK) return fail(st);
@@ -390,7 +457,8 @@ void rlb_engine_destroy(rlb_engine* e) {
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     void* bufs[] = {e->d_q, e->d_counts, e->d_etr, e->d_etr_il, e->d_vis, e->d_nvis, e->d_rng_n, e->d_eps, e->d_ucb_t, e->d_flag, e->d_env,
-                    e->d_trans, e->d_thr, e->d_thr_state, e->d_totals, e->d_flagword, e->d_episodes, e->d_sums};
+                    e->d_trans, e->d_thr, e->d_thr_state, e->d_totals, e->d_flagword, e->d_episodes, e->d_sums,
+                    e->d_model_ent, e->d_model_bits, e->d_model_len};
     for (void* b : bufs) if (b) cudaFree(b);
     for (void* b : e->d_stage) if (b) cudaFree(b);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -527,12 +595,13 @@ rlb_status rlb_agent_set_kind(rlb_engine* e, int32_t agent_kind) {
     const uint64_t N = e->cfg.n_agents;
     e->cfg.agent_kind = agent_kind;
     e->variant.trace = agent_kind == RLB_AGENT_TRACES ? 1 : 0;
-    if (e->variant.trace && !e->d_etr) {
-        const uint64_t by_steps = e->cfg.env_kind == RLB_ENV_BLACKJACK ? 32ull : (uint64_t)e->cfg.max_steps + 1ull;
-        const uint32_t vmax = (uint32_t)std::min<uint64_t>(e->S, by_steps);
-        CK(cudaMalloc(&e->d_etr, (size_t)N * vmax * e->APAD * e->real_size));
-        CK(cudaMalloc(&e->d_vis, (size_t)N * vmax * sizeof(uint16_t)));
-        e->dp.etr = e->d_etr; e->dp.vis = e->d_vis; e->dp.vmax = vmax;
+    {
+        rlb_status st0 = ensure_trace_buffers(e);
+        if (st0 != RLB_OK) return st0;
+        if (e->cfg.planning_steps) {   // the new agent is wrapped again, around an empty model
+            st0 = attach_model(e, e->cfg.planning_steps);
+            if (st0 != RLB_OK) return st0;
+        }
     }
     CK(fill_q_default(e));
     CK(fill<uint8_t>(e, e->d_flag, N, (uint8_t)1));
@@ -565,7 +634,103 @@ rlb_status rlb_policy_reset(rlb_engine* e) {
 rlb_status rlb_agent_reset(rlb_engine* e) {   // one_step_agent.rs:43-46: action_selection.reset(); policy.reset()
     rlb_status st = rlb_selector_reset(e);
     if (st != RLB_OK) return st;
-    return rlb_policy_reset(e);
+    st = rlb_policy_reset(e);
+    if (st != RLB_OK) return st;
+    return e->cfg.planning_steps ? rlb_model_reset(e) : RLB_OK;   // internal_model_agent.rs:81-84
+}
+
+rlb_status rlb_agent_set_model(rlb_engine* e, uint32_t planning_steps) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    if (planning_steps && e->cfg.store_kind != 0 && e->cfg.store_kind != STORE_GLOBAL) {
+        set_error("a Dyna model (planning_steps > 0) needs the HBM store");
+        return RLB_ERR_UNSUPPORTED;
+    }
+    rlb_status st = attach_model(e, planning_steps);
+    if (st != RLB_OK) return st;
+    return pick_store(e);
+}
+
+// ------------------------------------------------------------------------------- Model
+rlb_status rlb_model_add_info(rlb_engine* e, const uint32_t* obs, const uint32_t* action, const double* reward, const uint32_t* next_obs) {
+    if (!e || !obs || !action || !reward || !next_obs) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    if (!e->cfg.planning_steps) { set_error("no model attached (rlb_agent_set_model)"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    const void* in[4];
+    CK(stage_in(e, 0, obs, N * 4, &in[0]));
+    CK(stage_in(e, 1, action, N * 4, &in[1]));
+    CK(stage_in(e, 2, reward, N * 8, &in[2]));
+    CK(stage_in(e, 3, next_obs, N * 4, &in[3]));
+    k_model_add_info<<<(unsigned)((N + 127) / 128), 128, 0, e->stream>>>(e->dp, e->A, (const uint32_t*)in[0], (const uint32_t*)in[1],
+                                                                         (const double*)in[2], (const uint32_t*)in[3]);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+rlb_status rlb_model_get_info(rlb_engine* e, uint32_t* obs_out, uint32_t* action_out, uint32_t* next_obs_out, double* reward_out) {
+    if (!e || !obs_out || !action_out || !next_obs_out || !reward_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    if (!e->cfg.planning_steps) { set_error("no model attached (rlb_agent_set_model)"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    void* dev[4];
+    CK(stage_out(e, 0, obs_out, N * 4, &dev[0]));
+    CK(stage_out(e, 1, action_out, N * 4, &dev[1]));
+    CK(stage_out(e, 2, next_obs_out, N * 4, &dev[2]));
+    CK(stage_out(e, 3, reward_out, N * 8, &dev[3]));
+    CK(cudaMemsetAsync(e->d_flagword, 0, 4, e->stream));
+    k_model_get_info<<<(unsigned)((N + 127) / 128), 128, 0, e->stream>>>(e->dp, e->A, (uint32_t*)dev[0], (uint32_t*)dev[1], (uint32_t*)dev[2],
+                                                                         (double*)dev[3], e->d_flagword);
+    CK(cudaGetLastError());
+    uint32_t any = 0;
+    CK(cudaMemcpyAsync(&any, e->d_flagword, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(finish_out(e, obs_out, dev[0], N * 4));
+    CK(finish_out(e, action_out, dev[1], N * 4));
+    CK(finish_out(e, next_obs_out, dev[2], N * 4));
+    CK(finish_out(e, reward_out, dev[3], N * 8));
+    if (any) { set_error("RandomModel::get_info on an empty model (the reference panics: gen_range over an empty range)"); return RLB_ERR_INVALID_ARG; }
+    return RLB_OK;
+}
+rlb_status rlb_model_reset(rlb_engine* e) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    if (!e->cfg.planning_steps) return RLB_OK;
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    CK(cudaMemsetAsync(e->d_model_bits, 0, (size_t)N * e->dp.mwords * sizeof(uint32_t), e->stream));
+    CK(cudaMemsetAsync(e->d_model_len, 0, N * sizeof(uint32_t), e->stream));
+    return RLB_OK;
+}
+uint32_t rlb_model_capacity(const rlb_engine* e) { return e ? e->dp.mcap : 0u; }
+rlb_status rlb_download_model(rlb_engine* e, uint32_t* len_out, rlb_model_entry* entries_out) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    if (!e->cfg.planning_steps) { set_error("no model attached (rlb_agent_set_model)"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    if (len_out) CK(copy_out(e, len_out, e->d_model_len, N * 4));
+    if (entries_out) {
+        const size_t n_el = (size_t)N * e->dp.mcap;
+        void* dev;
+        CK(stage_out(e, 7, entries_out, n_el * sizeof(rlb_model_entry), &dev));
+        k_model_export<<<(unsigned)((n_el + 255) / 256), 256, 0, e->stream>>>(e->dp, e->A, (rlb_model_entry*)dev);
+        CK(cudaGetLastError());
+        CK(finish_out(e, entries_out, dev, n_el * sizeof(rlb_model_entry)));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+rlb_status rlb_upload_model(rlb_engine* e, const uint32_t* len, const rlb_model_entry* entries) {
+    if (!e || !len || !entries) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
+    if (!e->cfg.planning_steps) { set_error("no model attached (rlb_agent_set_model)"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    const uint64_t N = e->cfg.n_agents;
+    const void* in[2];
+    CK(stage_in(e, 0, len, N * 4, &in[0]));
+    CK(stage_in(e, 7, entries, (size_t)N * e->dp.mcap * sizeof(rlb_model_entry), &in[1]));
+    k_model_import<<<(unsigned)((N + 127) / 128), 128, 0, e->stream>>>(e->dp, e->A, (const uint32_t*)in[0], (const rlb_model_entry*)in[1]);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
 }
 
 static rlb_status run_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, uint64_t eval_at, rlb_train_out* out,
@@ -852,6 +1017,15 @@ double rlb_rng_uniform_f64(uint64_t seed, uint64_t agent_id, uint64_t* word_inde
 uint64_t rlb_rng_uniform_usize(uint64_t seed, uint64_t agent_id, uint64_t* word_index, uint64_t range) {
     if (range == 0) return host_u64(seed, agent_id, word_index);
     const uint64_t zone = UINT64_MAX - (UINT64_MAX - range + 1) % range;
+    for (;;) {
+        const uint64_t v = host_u64(seed, agent_id, word_index);
+        const unsigned __int128 m = (unsigned __int128)v * range;
+        if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
+    }
+}
+uint64_t rlb_rng_gen_range(uint64_t seed, uint64_t agent_id, uint64_t* word_index, uint64_t range) {
+    if (range == 0) return host_u64(seed, agent_id, word_index);
+    const uint64_t zone = (range << __builtin_clzll(range)) - 1;
     for (;;) {
         const uint64_t v = host_u64(seed, agent_id, word_index);
         const unsigned __int128 m = (unsigned __int128)v * range;

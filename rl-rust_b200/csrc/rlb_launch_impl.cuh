@@ -97,6 +97,16 @@ cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStre
 }
 
 template <int ENV>
+cudaError_t launch_run_model(const Variant& v, const DevParams& p, cudaStream_t stream) {
+    const unsigned grid = grid_for(p.n_agents);
+    const size_t smem = EnvTab<ENV>::smem_bytes(p.S);
+#define RLB_CALL(R, P, SL, T) k_run<ENV, R, P, SL, T, STORE_GLOBAL, true><<<grid, kBlock, smem, stream>>>(p)
+    RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+    return cudaGetLastError();
+}
+
+template <int ENV>
 cudaError_t run_kernel_attributes(const Variant& v, int store, cudaFuncAttributes* attr) {
     if (store == STORE_HYBRID) {
         if constexpr (SmemCapable<ENV>::value) {
@@ -176,5 +186,7 @@ cudaError_t launch_step(StepOp op, const Variant& v, const DevParams& p, const S
     template size_t smem_store_bytes<ENV>(const Variant&, int, uint32_t, uint32_t, uint32_t);                           \
     template cudaError_t launch_step<ENV>(StepOp, const Variant&, const DevParams&, const StepArgs&, cudaStream_t); \
     template cudaError_t run_kernel_attributes<ENV>(const Variant&, int, cudaFuncAttributes*);
+
+#define RLB_INSTANTIATE_ENV_MODEL(ENV) template cudaError_t launch_run_model<ENV>(const Variant&, const DevParams&, cudaStream_t);
 
 }   // namespace rlb

@@ -112,6 +112,12 @@ __global__ void __launch_bounds__(128) k_update(const DevParams p, const uint32_
     Real pred[Core::A], vals[Core::A];
     core.rows(s2[i], pred, vals);
     Real td = core.update(s[i], a[i], (Real)reward[i], term[i] != 0, s2[i], a2[i], vals, p);
+    if (p.planning_steps) {   // InternalModelAgent::update (internal_model_agent.rs:62-77)
+        RandomModelDev model;
+        model.load(p, i);
+        learn_and_plan(core, model, s[i], a[i], (Real)reward[i], s2[i], p);
+        model.save(p, i);
+    }
     if (td_out) td_out[i] = td;
     core.save(p, i);
 }
@@ -172,6 +178,58 @@ __global__ void __launch_bounds__(128) k_selector_probs(const DevParams p, const
     core.probs(obs[i], v, pr, p);
 #pragma unroll
     for (int k = 0; k < Core::A; ++k) probs_out[i * Core::A + k] = pr[k];
+}
+
+// Model::add_info (random_model.rs:37-41)
+static __global__ void k_model_add_info(const DevParams p, uint32_t A, const uint32_t* s, const uint32_t* a, const double* reward, const uint32_t* s2) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    RandomModelDev model;
+    model.load(p, i);
+    model.add_info(s[i] * A + a[i], s2[i], (float)reward[i]);
+    model.save(p, i);
+}
+// Model::get_info (random_model.rs:27-35); agents with an empty model are flagged and draw nothing
+static __global__ void k_model_get_info(const DevParams p, uint32_t A, uint32_t* s, uint32_t* a, uint32_t* s2, double* reward, uint32_t* any_empty) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    RandomModelDev model;
+    model.load(p, i);
+    if (model.len == 0) { atomicOr(any_empty, 1u); return; }
+    Rng rng;
+    rng.init(p.seed, p.first_agent + i, p.rng_n[i]);
+    const uint2 info = model.get_info(rng);
+    p.rng_n[i] = rng.n;
+    const uint32_t key = info.x & 0xffffu;
+    s[i] = key / A; a[i] = key % A; s2[i] = info.x >> 16; reward[i] = (double)__uint_as_float(info.y);
+}
+// model snapshots: device layout <-> rlb_model_entry [N][mcap]
+static __global__ void k_model_export(const DevParams p, uint32_t A, rlb_model_entry* out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.n_agents * p.mcap) return;
+    const uint64_t i = idx / p.mcap;
+    const uint32_t j = (uint32_t)(idx % p.mcap);
+    rlb_model_entry en{0u, 0u, 0u, 0.0f};
+    if (j < p.model_len[i]) {
+        const uint2 info = p.model_ent[idx];
+        const uint32_t key = info.x & 0xffffu;
+        en = rlb_model_entry{key / A, key % A, info.x >> 16, __uint_as_float(info.y)};
+    }
+    out[idx] = en;
+}
+static __global__ void k_model_import(const DevParams p, uint32_t A, const uint32_t* len, const rlb_model_entry* in) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_agents) return;
+    uint32_t* bits = p.model_bits + i * p.mwords;
+    for (uint32_t w = 0; w < p.mwords; ++w) bits[w] = 0u;
+    const uint32_t n = len[i] < p.mcap ? len[i] : p.mcap;
+    for (uint32_t j = 0; j < n; ++j) {
+        const rlb_model_entry en = in[i * p.mcap + j];
+        const uint32_t key = en.obs * A + en.action;
+        bits[key >> 5] |= 1u << (key & 31u);
+        p.model_ent[i * p.mcap + j] = make_uint2(key | (en.next_obs << 16), __float_as_uint(en.reward));
+    }
+    p.model_len[i] = n;
 }
 
 // ActionSelection::update for eps-greedy: decay_epsilon (uniform_epsilon_greed.rs:42-49)

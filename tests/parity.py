@@ -27,7 +27,7 @@ def all_combos(envs=(0, 1, 2, 3), agents=(0, 1), selectors=(0, 1), policies=(0, 
 def hyper(n_episodes, **over):
     """The reference CLI's defaults (bin/taxi.rs:22-68) with the decay derived from n_episodes (:78)."""
     h = dict(map_id=1, slippery=True, max_steps=100, lr=0.05, gamma=0.95, lambda_=0.5, eps0=1.0,
-             eps_decay=1.0 / (0.5 * n_episodes), eps_final=0.0, ucb_c=0.5, default_q=0.0, decay_kind=0, seed=0x5EED0001)
+             eps_decay=1.0 / (0.5 * n_episodes), eps_final=0.0, ucb_c=0.5, default_q=0.0, decay_kind=0, seed=0x5EED0001, planning_steps=0)
     h.update(over)
     return h
 
@@ -37,7 +37,8 @@ def oracle_config(c, h):
                          policy=c["policy"], selector=c["selector"], target=c["target"], agent=c["agent"],
                          real=c["real"], decay_kind=h["decay_kind"], lr=h["lr"], gamma=h["gamma"],
                          lambda_=h["lambda_"], eps0=h["eps0"], eps_decay=h["eps_decay"], eps_final=h["eps_final"],
-                         ucb_c=h["ucb_c"], default_q=h["default_q"], seed=h["seed"])
+                         ucb_c=h["ucb_c"], default_q=h["default_q"], seed=h["seed"],
+                         planning_steps=h.get("planning_steps", 0))
 
 
 def make_engine(c, h, n_agents, first_agent_id=0, **kw):
@@ -47,7 +48,7 @@ def make_engine(c, h, n_agents, first_agent_id=0, **kw):
                       decay_kind=h["decay_kind"], learning_rate=h["lr"], discount_factor=h["gamma"],
                       lambda_factor=h["lambda_"], initial_epsilon=h["eps0"], epsilon_decay=h["eps_decay"],
                       final_epsilon=h["eps_final"], confidence_level=h["ucb_c"], default_value=h["default_q"],
-                      seed=h["seed"], first_agent_id=first_agent_id, **kw)
+                      seed=h["seed"], first_agent_id=first_agent_id, planning_steps=h.get("planning_steps", 0), **kw)
 
 
 def bits_equal(a, b):
@@ -92,12 +93,15 @@ def gpu_run(c, h, n_agents, n_episodes, eval_at, first_agent_id=0, traj_capacity
             res = {}
         q, counts = eng.download_tables()
         st = eng.states()
+        model = eng.download_model() if h.get("planning_steps", 0) else None
     out = dict(ret=eps["ret"].T.astype(np.float64), len=eps["length"].T.astype(np.uint64),
                tdsum=eps["td_sum"].T.astype(np.float64), tdabs=eps["td_abs_sum"].T.astype(np.float64),
                q=q.astype(np.float64), counts=counts.astype(np.uint64), state=st, sums=sums,
                train_steps=train_steps, eval_steps=eval_steps)
     if traj_capacity:
         out["traj"], out["traj_count"] = res["traj"], res["traj_count"]
+    if model is not None:
+        out["model_len"], out["model"] = model
     return out
 
 
