@@ -48,6 +48,10 @@ WORKLOADS = {
     "c4": dict(desc="Taxi one-step Q-learning, eps-greedy, Basic", env=3, agent=0, selector=0, policy=0, target=1,
                agents_per_gpu=1 << 21, n_episodes=1000, chunk=100),
 }
+# not a BASELINE config: the crate's Dyna bin (src/bin/cliffwalking_model.rs), "next" row N4 of SURVEY.md §8(f)
+WORKLOADS["dyna"] = dict(desc="CliffWalking one-step Dyna-Q (InternalModelAgent, RandomModel, 10 planning steps), eps-greedy, Basic",
+                         env=2, agent=0, selector=0, policy=0, target=1, planning_steps=10, agents_per_gpu=1 << 20, n_episodes=200,
+                         chunk=20)
 # C5, the full sweep: 4 envs x {Sarsa, Q, Expected Sarsa one-step; Sarsa(lambda), Q(lambda)} x {eps-greedy, UCB} x
 # {Basic, Double} = 80 cells, every cell an engine of its own on every GPU, one metric gather per cell per step.
 WORKLOADS["c5"] = dict(desc="full sweep: 4 envs x 5 update rules x {eps-greedy, UCB} x {Basic, Double} = 80 cells", cells=[
@@ -66,6 +70,9 @@ def algorithmic_bytes(w, real_size, train_steps, trace_rows):
     per_step = ((2 * A + 3) * R + 2) if w["policy"] else ((A + 2) * R + 2)
     if w["selector"]:
         per_step += 4 * A + 8
+    k = w.get("planning_steps", 0)
+    if k:   # Dyna: membership word + k replays, each one 8-byte model entry and one more update
+        per_step = per_step * (1 + k) + 8 * k + 4
     return train_steps * per_step + trace_rows * 4 * R * A
 
 
@@ -139,7 +146,7 @@ def measured_traffic(workload, agents_per_gpu, dtype):
 
 def workload_hyper(w):
     import parity as P
-    return P.hyper(w["n_episodes"], slippery=w.get("slippery", False))
+    return P.hyper(w["n_episodes"], slippery=w.get("slippery", False), planning_steps=w.get("planning_steps", 0))
 
 
 def combo(w, real):

@@ -190,6 +190,19 @@ class Agent {
         check(rlb_agent_get_action(need(), obs.data(), a.data()));
         return a;
     }
+    // agent.rs:54-62; reward as f64, the returned temporal differences widened to f64
+    std::vector<double> update(const std::vector<uint32_t>& curr_obs, const std::vector<uint32_t>& curr_action, const std::vector<double>& reward,
+                               const std::vector<uint8_t>& terminated, const std::vector<uint32_t>& next_obs, const std::vector<uint32_t>& next_action) {
+        std::vector<double> td(curr_obs.size());
+        if (cfg_.real_kind == RLB_REAL_F64) {
+            check(rlb_agent_update(need(), curr_obs.data(), curr_action.data(), reward.data(), terminated.data(), next_obs.data(), next_action.data(), td.data()));
+        } else {
+            std::vector<float> t32(curr_obs.size());
+            check(rlb_agent_update(need(), curr_obs.data(), curr_action.data(), reward.data(), terminated.data(), next_obs.data(), next_action.data(), t32.data()));
+            for (size_t i = 0; i < t32.size(); ++i) td[i] = t32[i];
+        }
+        return td;
+    }
     void reset() { if (engine_) check(rlb_agent_reset(engine_->get())); }    // agent.rs:64
 
     // agent.rs:66-118.  [agent-major] vectors of n_agents * n_episodes entries (just n_episodes for one agent).
@@ -261,6 +274,7 @@ class Agent {
     }
 
    private:
+    friend class InternalModelAgent;
     void bind(Env& env) {
         if (engine_) {
             if (env.engine() != engine_) throw std::logic_error("agent is already bound to another env");
@@ -292,6 +306,89 @@ class ElegibilityTracesAgent : public Agent {   // agent/elegibility_traces_agen
     ElegibilityTracesAgent(const TabularPolicy& policy, double discount_factor, const ActionSelection& action_selection,
                            double lambda_factor, GetNextQValue f, const Batch& batch = Batch())
         : Agent(policy, discount_factor, action_selection, lambda_factor, f, RLB_AGENT_TRACES, batch) {}
+};
+
+// ---------------------------------------------------------------------------------- Model<T, COUNT>  (model.rs:12-16)
+class RandomModel {   // model/random_model.rs:9-45 — lives on the device, next to the agent its InternalModelAgent borrows
+   public:
+    struct Info { std::vector<uint32_t> obs, action, next_obs; std::vector<double> reward; };   // (state, action, next_state, reward)
+    Info get_info() {                                                                      // :27-35
+        const size_t n = agents();
+        Info r{std::vector<uint32_t>(n), std::vector<uint32_t>(n), std::vector<uint32_t>(n), std::vector<double>(n)};
+        check(rlb_model_get_info(need(), r.obs.data(), r.action.data(), r.next_obs.data(), r.reward.data()));
+        return r;
+    }
+    void add_info(const std::vector<uint32_t>& obs, const std::vector<uint32_t>& action, const std::vector<double>& reward,
+                  const std::vector<uint32_t>& next_obs) {                                 // :37-41
+        check(rlb_model_add_info(need(), obs.data(), action.data(), reward.data(), next_obs.data()));
+    }
+    void reset() { check(rlb_model_reset(need())); }                                       // :43-45
+    // remembered transitions of every agent, in insertion order: len [n_agents], entries [n_agents][capacity]
+    std::pair<std::vector<uint32_t>, std::vector<rlb_model_entry>> entries() {
+        const size_t n = agents(), cap = rlb_model_capacity(need());
+        std::vector<uint32_t> len(n);
+        std::vector<rlb_model_entry> ent(n * cap);
+        check(rlb_download_model(need(), len.data(), ent.data()));
+        return {len, ent};
+    }
+
+   private:
+    friend class InternalModelAgent;
+    rlb_engine* need() const {
+        if (!engine_) throw std::logic_error("the model is bound when its InternalModelAgent first sees an env");
+        return engine_->get();
+    }
+    size_t agents() const { return n_agents_; }
+    Engine* engine_ = nullptr;
+    size_t n_agents_ = 0;
+};
+
+// agent/internal_model_agent.rs:9-85 — Dyna.  Borrows `agent` (which keeps what it has learned) and `model` for its
+// lifetime, like the `&'a mut dyn Agent` of the reference; planning_length must be > 0.
+class InternalModelAgent {
+   public:
+    InternalModelAgent(Agent& agent, RandomModel& model, uint32_t planning_length) : agent_(agent), model_(model), planning_(planning_length) {
+        if (!planning_length) throw std::invalid_argument("planning_length must be > 0");
+        if (agent_.engine_) attach();
+    }
+    ~InternalModelAgent() {   // end of the borrow: the agent carries on without a model
+        if (agent_.engine_ && model_.engine_ == agent_.engine_) rlb_agent_set_model(agent_.engine_->get(), 0);
+        model_.engine_ = nullptr;
+    }
+    InternalModelAgent(const InternalModelAgent&) = delete;
+    InternalModelAgent& operator=(const InternalModelAgent&) = delete;
+    void set_future_q_value_func(GetNextQValue f) { agent_.set_future_q_value_func(f); }          // :34-36
+    void set_action_selector(const ActionSelection& s) { agent_.set_action_selector(s); }         // :38-40
+    std::vector<uint32_t> get_action(const std::vector<uint32_t>& obs) { return agent_.get_action(obs); }   // :42-44
+    std::vector<double> update(const std::vector<uint32_t>& curr_obs, const std::vector<uint32_t>& curr_action, const std::vector<double>& reward,
+                               const std::vector<uint8_t>& terminated, const std::vector<uint32_t>& next_obs,
+                               const std::vector<uint32_t>& next_action) {                        // :46-79
+        attach();
+        return agent_.update(curr_obs, curr_action, reward, terminated, next_obs, next_action);
+    }
+    void reset() { agent_.reset(); }                                                              // :81-84 (the engine empties the attached model too)
+    TrainResult train(Env& env, uint64_t n_episodes, uint64_t eval_at) {
+        agent_.bind(env);
+        attach();
+        return agent_.train(env, n_episodes, eval_at);
+    }
+    EvalResult evaluate(Env& env, uint64_t n_episodes) {
+        agent_.bind(env);
+        attach();
+        return agent_.evaluate(env, n_episodes);
+    }
+
+   private:
+    void attach() {
+        if (!agent_.engine_) throw std::logic_error("agent is not bound yet: train or evaluate on an env first");
+        if (model_.engine_ == agent_.engine_) return;
+        check(rlb_agent_set_model(agent_.engine_->get(), planning_));
+        model_.engine_ = agent_.engine_;
+        model_.n_agents_ = agent_.cfg_.n_agents;
+    }
+    Agent& agent_;
+    RandomModel& model_;
+    uint32_t planning_;
 };
 
 }   // namespace rlrust

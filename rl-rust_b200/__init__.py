@@ -10,9 +10,9 @@ from . import _abi as abi
 from ._abi import Engine, EnvNotReady, RlbError
 from .snapshot import load_snapshot, save_snapshot
 from .api import (BlackJackEnv, CliffWalkingEnv, DoubleTabularPolicy, ElegibilityTracesAgent, Env, FrozenLakeEnv,
-                  OneStepAgent, TabularPolicy, TaxiEnv, UniformEpsilonGreed, UpperConfidenceBound, expected_sarsa,
+                  InternalModelAgent, OneStepAgent, RandomModel, TabularPolicy, TaxiEnv, UniformEpsilonGreed, UpperConfidenceBound, expected_sarsa,
                   qlearning, sarsa)
 
 __all__ = ["abi", "Engine", "save_snapshot", "load_snapshot", "EnvNotReady", "RlbError", "BlackJackEnv", "CliffWalkingEnv", "DoubleTabularPolicy",
-           "ElegibilityTracesAgent", "Env", "FrozenLakeEnv", "OneStepAgent", "TabularPolicy", "TaxiEnv",
+           "ElegibilityTracesAgent", "Env", "FrozenLakeEnv", "InternalModelAgent", "OneStepAgent", "RandomModel", "TabularPolicy", "TaxiEnv",
            "UniformEpsilonGreed", "UpperConfidenceBound", "expected_sarsa", "qlearning", "sarsa"]

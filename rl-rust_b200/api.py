@@ -293,3 +293,81 @@ class ElegibilityTracesAgent(_Agent):
 
     def __init__(self, policy, discount_factor, action_selection, lambda_factor, get_next_q_value, **kw):
         super().__init__(policy, discount_factor, action_selection, lambda_factor, get_next_q_value, **kw)
+
+
+# --------------------------------------------------------------------------- Model<T, COUNT> / Dyna
+class RandomModel:
+    """model/random_model.rs:9-45 — first-seen transitions `(obs, action) -> (next_obs, reward)` in insertion order.
+    Lives on the device next to the agent it is given to (InternalModelAgent binds it)."""
+
+    def __init__(self):
+        self._engine = None
+
+    def _need(self):
+        if self._engine is None:
+            raise RuntimeError("the model is bound when its InternalModelAgent first sees an env")
+        return self._engine
+
+    def get_info(self):             # model.rs:13 — (state, action, next_state, reward), index drawn with gen_range
+        obs, action, next_obs, reward = self._need().model_get_info()
+        return obs, action, next_obs, reward
+
+    def add_info(self, obs, action, reward, next_obs):   # model.rs:14
+        self._need().model_add_info(obs, action, reward, next_obs)
+
+    def reset(self):                # model.rs:15
+        self._need().model_reset()
+
+    def entries(self):
+        """(len [n_agents], entries [n_agents, capacity]) snapshot of the remembered transitions."""
+        return self._need().download_model()
+
+
+class InternalModelAgent:
+    """agent/internal_model_agent.rs:9-85 — Dyna: `InternalModelAgent::new(agent, model, planning_length)` borrows an
+    agent (which keeps whatever it has learned) and, after each of its updates, remembers the transition and replays
+    `planning_length` remembered ones.  planning_length must be > 0 here (0 is the plain agent)."""
+
+    def __init__(self, agent, model, planning_length):
+        if int(planning_length) <= 0:
+            raise ValueError("planning_length must be > 0")
+        self.agent, self.model, self.planning_steps = agent, model, int(planning_length)
+        if agent.engine is not None:
+            self._attach()
+
+    def _attach(self):
+        if self.model._engine is not self.agent.engine:
+            self.agent.engine.set_model(self.planning_steps)
+            self.model._engine = self.agent.engine
+
+    def set_future_q_value_func(self, func):             # :34-36
+        self.agent.set_future_q_value_func(func)
+
+    def set_action_selector(self, action_selector):      # :38-40
+        self.agent.set_action_selector(action_selector)
+
+    def get_action(self, obs):                           # :42-44
+        return self.agent.get_action(obs)
+
+    def update(self, curr_obs, curr_action, reward, terminated, next_obs, next_action):   # :46-79
+        self._attach()
+        return self.agent.update(curr_obs, curr_action, reward, terminated, next_obs, next_action)
+
+    def reset(self):                                     # :81-84
+        self.agent.reset()                               # the engine empties the attached model with it
+
+    def train(self, env, n_episodes, eval_at, **kw):
+        self.agent._bind(env)
+        self._attach()
+        return self.agent.train(env, n_episodes, eval_at, **kw)
+
+    def evaluate(self, env, n_episodes):
+        self.agent._bind(env)
+        self._attach()
+        return self.agent.evaluate(env, n_episodes)
+
+    def release(self):
+        """End of the borrow (the wrapper going out of scope in the reference): the agent carries on without a model."""
+        if self.agent.engine is not None and self.model._engine is self.agent.engine:
+            self.agent.engine.set_model(0)
+        self.model._engine = None

@@ -1,5 +1,6 @@
 """Host experiment driver — the reference's per-env bins over the engine ("next" row N1/N2 of SURVEY.md §8f).
 
+`run_model_experiment()` is `main()` of src/bin/cliffwalking_model.rs (Q-learning against Dyna-Q).
 `run_experiment()` is `main()` of src/bin/{taxi,frozen_lake,cliffwalking,blackjack}.rs with the same flags and
 defaults (bin/taxi.rs:22-68): two agents (OneStepAgent, ElegibilityTracesAgent) x two selectors (eps-greedy, UCB) x
 three bootstrap targets = 12 runs, each `train(n, n/10)` -> `evaluate(n)` -> `agent.reset()` (bin/taxi.rs:158-203), the
@@ -115,10 +116,58 @@ def run_experiment(env_name, *, n_agents=1, seed=0x5EED0001, real="f64", device=
     return out
 
 
+LEGENDS_MODEL = ["ε-Greedy One-Step Qlearning", "ε-Greedy One-Step Dyna-Qlearning"]   # bin/cliffwalking_model.rs:96-111
+
+
+def run_model_experiment(*, n_agents=1, seed=0x5EED0001, real="f64", device=0, planning_steps=10, verbose=True, **flags):
+    """`main()` of src/bin/cliffwalking_model.rs: CliffWalking, a OneStepAgent with qlearning and then an
+    InternalModelAgent (RandomModel, 10 planning steps) around a second such agent, eps-greedy, Basic policy; each
+    `train(n, n/10)` -> `evaluate(n)` -> `reset()` on the one shared env (:158-203).  Same output dict as run_experiment."""
+    f = dict(DEFAULTS)
+    f.update(flags)
+    n = int(f["n_episodes"])
+    epsilon_decay = f["initial_epsilon"] / (f["exploration_time"] * n)                               # :77
+    window = max(1, n // int(f["moving_average_window"]))
+    env = api.CliffWalkingEnv(f["max_steps"])                                                        # :86
+    eng = abi.Engine(env.kind, n_agents=n_agents, policy=abi.POLICY_BASIC, selector=abi.SEL_EPS_GREEDY, target=abi.TARGET_QLEARNING,
+                     agent=abi.AGENT_ONE_STEP, real=abi.REAL_F32 if real == "f32" else abi.REAL_F64, learning_rate=f["learning_rate"],
+                     discount_factor=f["discount_factor"], lambda_factor=f["lambda_factor"], initial_epsilon=f["initial_epsilon"],
+                     decay_kind=abi.DECAY_SUB, epsilon_decay=epsilon_decay, final_epsilon=f["final_epsilon"],
+                     confidence_level=f["confidence_level"], default_value=0.0, seed=seed, device=device, **env._cfg())
+    env.bind(eng)
+    out = dict(legends=LEGENDS_MODEL, train_rewards=[], train_episodes_length=[], train_errors=[], test_rewards=[],
+               test_episodes_length=[], seconds=[], train_steps=[])
+    for i, planning in enumerate((0, int(planning_steps))):                                          # :158-160
+        eng.set_agent_kind(abi.AGENT_ONE_STEP)                                                       # `one_step_agent` / `other` (:136-148): a fresh agent
+        if planning:
+            eng.set_model(planning)                                                                  # :150-156
+        eng.set_selector(abi.SEL_EPS_GREEDY)                                                         # :164
+        t0 = time.perf_counter()
+        res = eng.train(n, max(1, n // 10))                                                          # :166-167
+        dt = time.perf_counter() - t0
+        if verbose:
+            print("%s %.2fs (%d agents, %.3g train steps/s)" % (LEGENDS_MODEL[i], dt, n_agents, res["train_steps"] / dt))
+        s_ = res["sums"]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean_td = s_[:, 2] / s_[:, 0]
+        out["train_errors"].append(moving_average(window, mean_td))
+        out["train_rewards"].append(moving_average(window, s_[:, 1] / n_agents))
+        out["train_episodes_length"].append(moving_average(window, s_[:, 0] / n_agents))
+        out["seconds"].append(dt)
+        out["train_steps"].append(int(res["train_steps"]))
+        ev = eng.evaluate(n, sums=True)["sums"]                                                      # :189
+        out["test_rewards"].append(moving_average(window, ev[:, 1] / n_agents))
+        out["test_episodes_length"].append(moving_average(window, ev[:, 0] / n_agents))
+        eng.agent_reset()                                                                            # :201
+    out["final_rng_n"] = [int(x) for x in eng.states()["rng_n"][:8]]
+    eng.close()
+    return out
+
+
 def main(argv=None):
     import argparse
-    ap = argparse.ArgumentParser(description="RL-Rust bins over the B200 engine: blackjack | frozen_lake | cliffwalking | taxi")
-    ap.add_argument("env", choices=["blackjack", "frozen_lake", "cliffwalking", "taxi"])
+    ap = argparse.ArgumentParser(description="RL-Rust bins over the B200 engine: blackjack | frozen_lake | cliffwalking | taxi | cliffwalking_model")
+    ap.add_argument("env", choices=["blackjack", "frozen_lake", "cliffwalking", "taxi", "cliffwalking_model"])
     ap.add_argument("--n_episodes", "-n", type=int, default=DEFAULTS["n_episodes"])
     for name in ("max_steps", "moving_average_window"):
         ap.add_argument("--" + name, type=int, default=DEFAULTS[name])
@@ -136,7 +185,12 @@ def main(argv=None):
     a = vars(ap.parse_args(argv))
     env_name, outp = a.pop("env"), a.pop("out")
     a.pop("show_example")
-    res = run_experiment(env_name, **a)
+    if env_name == "cliffwalking_model":
+        for k in ("tally_games", "stochastic_env", "map"):
+            a.pop(k)
+        res = run_model_experiment(**a)
+    else:
+        res = run_experiment(env_name, **a)
     if outp:
         with open(outp, "w") as fh:
             json.dump(res, fh)

@@ -65,6 +65,26 @@ int main(int argc, char** argv) {
         std::printf("B.totals %" PRIu64 " %" PRIu64 " store=%u\n", tracer.last_train().train_steps, tracer.last_train().eval_steps,
                     rlb_engine_store_kind(tracer.engine()->get()));
         dump("B.lengths", l3);
+
+        // --- bin/cliffwalking_model.rs in miniature: Dyna-Q around a second agent, two streams, f64
+        CliffWalkingEnv cliff(100);
+        Batch b3;
+        b3.n_agents = 2; b3.seed = 0xD17A;
+        UniformEpsilonGreed eg3(1.0, Decay::sub(1.0 / (0.5 * 30.0)), 0.0);
+        OneStepAgent other(policy, 0.95, eg3, qlearning, b3);
+        RandomModel model;
+        {
+            InternalModelAgent model_agent(other, model, 10);                              // bin/cliffwalking_model.rs:152-156
+            auto [r4, l4, e4] = model_agent.train(cliff, 30, 3);
+            dump("C.lengths", l4); dump("C.errors", e4);
+            auto [len, ent] = model.entries();
+            std::printf("C.model %u %u | %u %u %u %.1f\n", len[0], len[1], ent[0].obs, ent[0].action, ent[0].next_obs, ent[0].reward);
+            auto info = model.get_info();
+            std::printf("C.info %u %u %u %.1f\n", info.obs[0], info.action[0], info.next_obs[0], info.reward[0]);
+        }
+        auto [r5, l5, e5] = other.train(cliff, 5, 5);                                      // the borrow has ended: plain Q-learning again
+        dump("C.after", l5);
+        try { model.reset(); std::printf("C no-throw\n"); } catch (const std::logic_error&) { std::printf("C model unbound -> logic_error\n"); }
     } catch (const std::exception& e) {
         std::printf("FAILED: %s\n", e.what());
         return 1;

@@ -39,7 +39,7 @@ def test_mirror_results_equal_oracle():
     out = subprocess.check_output([EXE], text=True)
     assert "FAILED" not in out and "no-throw" not in out
     assert "A eval_at==0 -> domain_error" in out and "A step after termination -> EnvNotReady" in out
-    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l[0] in "AB" and "." in l.split()[0]}
+    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l[0] in "ABC" and "." in l.split()[0]}
     n = 60
     cfg = O.make_config(O.ENV_TAXI, target=O.TARGET_QLEARNING, eps_decay=1.0 / (0.5 * n), seed=0xC0DE)
     sessions = [O.Session(cfg, i) for i in range(3)]
@@ -65,3 +65,24 @@ def test_mirror_results_equal_oracle():
     tot = next(l for l in out.splitlines() if l.startswith("B.totals")).split()
     assert int(tot[1]) == o["train_steps"] and int(tot[2]) == o["eval_steps"] and tot[3] == "store=3"
     assert np.array_equal(np.array(lines["B.lengths"], np.uint64).reshape(40, 20), o["len"])
+    # C: Dyna-Q through InternalModelAgent / RandomModel, then the plain agent again once the borrow ended
+    assert "C model unbound -> logic_error" in out
+    cfg = O.make_config(O.ENV_CLIFF_WALKING, target=O.TARGET_QLEARNING, eps_decay=1.0 / (0.5 * 30), seed=0xD17A, planning_steps=10)
+    lens, errs, after = (np.array(lines["C.lengths"], np.uint64).reshape(2, 30), f64s(lines["C.errors"]).reshape(2, 30),
+                         np.array(lines["C.after"], np.uint64).reshape(2, 5))
+    for i in range(2):
+        s = O.Session(cfg, i)
+        r, l, t, _ = s.train(30, 3)
+        assert np.array_equal(lens[i], l) and P.bits_equal(errs[i], t)
+        ms, ma, ms2, mr = s.model()
+        assert int(lines["C.model"][i]) == len(ms)
+        if i == 0:
+            assert [int(x) for x in lines["C.model"][3:6]] == [ms[0], ma[0], ms2[0]] and float(lines["C.model"][6]) == mr[0]
+            info = s.model_get_info()
+            assert [int(x) for x in lines["C.info"][:3]] == list(info[:3]) and float(lines["C.info"][3]) == info[3]
+        else:
+            s.model_get_info()      # the batched call draws on every agent's stream
+        s.set_planning(0)
+        r, l, t, _ = s.train(5, 5)
+        assert np.array_equal(after[i], l)
+        s.close()

@@ -52,3 +52,30 @@ def test_twelve_run_matrix_matches_oracle(env_name, env_kind):
                 i += 1
     assert res["final_rng_n"][0] == s.export()[2].rng_n
     s.close()
+
+
+@pytest.mark.gpu
+def test_cliffwalking_model_bin_matches_oracle():
+    """bin/cliffwalking_model.rs:158-203 with n_agents = 1: Q-learning, then Dyna-Q (10 planning steps) around a second
+    fresh agent, on one env and one stream."""
+    drv = importlib.import_module("rl-rust_b200.driver")
+    n, seed = 60, 0xD17A
+    res = drv.run_model_experiment(n_agents=1, seed=seed, real="f64", verbose=False, n_episodes=n, moving_average_window=10)
+    cfg = O.make_config(O.ENV_CLIFF_WALKING, target=O.TARGET_QLEARNING, eps_decay=1.0 / (0.5 * n), seed=seed)
+    s = O.Session(cfg, 0)
+    window = n // 10
+    for i, planning in enumerate((0, 10)):
+        s.set_agent_kind(0)
+        s.set_planning(planning)
+        s.set_selector(0)
+        ret, ln, tds, _ = s.train(n, n // 10)
+        assert res["train_steps"][i] == int(ln.sum())
+        assert res["train_rewards"][i] == drv.moving_average(window, ret)
+        assert res["train_episodes_length"][i] == drv.moving_average(window, ln.astype(np.float64))
+        eret, eln = s.evaluate(n)
+        assert res["test_rewards"][i] == drv.moving_average(window, eret)
+        assert res["test_episodes_length"][i] == drv.moving_average(window, eln.astype(np.float64))
+        s.agent_reset()
+    assert res["final_rng_n"][0] == s.export()[2].rng_n
+    assert sum(res["train_episodes_length"][1]) < sum(res["train_episodes_length"][0])   # planning pays
+    s.close()

@@ -83,3 +83,43 @@ def test_trace_agent_through_the_mirror(rlb):
     assert agent.engine.cfg.store_kind == 0 and rlb.abi.lib.rlb_engine_store_kind(agent.engine.h) == 3   # auto -> hybrid store
     q, _ = agent.engine.download_tables()
     assert P.bits_equal(q.astype(np.float64), o["q"])
+
+
+def test_dyna_through_the_mirror(rlb):
+    """bin/cliffwalking_model.rs:136-203: `other` wrapped as InternalModelAgent(other, RandomModel, 10); train, evaluate,
+    the Model trait on its own, reset, and the end of the borrow."""
+    n_agents, n_ep, seed = 5, 24, 0xD17A
+    decay = 1.0 / (0.5 * n_ep)
+    env = rlb.CliffWalkingEnv(100)
+    other = rlb.OneStepAgent(rlb.TabularPolicy(0.05, 0.0), 0.95, rlb.UniformEpsilonGreed(1.0, ("sub", decay), 0.0), rlb.qlearning,
+                             n_agents=n_agents, seed=seed, real="f64")
+    model = rlb.RandomModel()
+    with pytest.raises(RuntimeError):
+        model.reset()                                   # not bound yet
+    with pytest.raises(ValueError):
+        rlb.InternalModelAgent(other, model, 0)
+    model_agent = rlb.InternalModelAgent(other, model, 10)
+    rewards, lengths, errors = model_agent.train(env, n_ep, n_ep // 10)
+    ev_rewards, ev_lengths = model_agent.evaluate(env, 6)
+    sessions = [O.Session(O.make_config(O.ENV_CLIFF_WALKING, target=O.TARGET_QLEARNING, eps_decay=decay, seed=seed, planning_steps=10), i)
+                for i in range(n_agents)]
+    ln_m, ent = model.entries()
+    info = model.get_info()
+    for i, s in enumerate(sessions):
+        ret, ln, tds, _ = s.train(n_ep, n_ep // 10)
+        eret, eln = s.evaluate(6)
+        assert np.array_equal(lengths[i], ln) and np.array_equal(rewards[i], ret) and P.bits_equal(errors[i], tds)
+        assert np.array_equal(ev_lengths[i], eln) and np.array_equal(ev_rewards[i], eret)
+        ms, ma, ms2, mr = s.model()
+        assert int(ln_m[i]) == len(ms) and np.array_equal(ent[i, :len(ms)]["next_obs"], ms2)
+        assert tuple(float(x[i]) for x in info) == tuple(float(x) for x in s.model_get_info())
+    model_agent.reset()
+    assert not model.entries()[0].any()
+    model_agent.release()
+    rewards, lengths, errors = other.train(env, 4, 2)   # plain Q-learning again, tables reset, stream carried on
+    for i, s in enumerate(sessions):
+        s.agent_reset()
+        s.set_planning(0)
+        ret, ln, tds, _ = s.train(4, 2)
+        assert np.array_equal(lengths[i], ln) and P.bits_equal(errors[i], tds)
+        s.close()
