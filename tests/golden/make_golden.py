@@ -26,12 +26,15 @@ CASES = {
     "c4_taxi_q_eps_basic": dict(env=3, agent=0, selector=0, policy=0, target=1),
     "x_taxi_qlambda_ucb_double": dict(env=3, agent=1, selector=1, policy=1, target=1),
     "x_blackjack_expsarsa_lambda_eps_double": dict(env=0, agent=1, selector=0, policy=1, target=2),
+    # Dyna (agent/internal_model_agent.rs): the bin's cell (bin/cliffwalking_model.rs) and one with every switch flipped
+    "d_cliff_dynaq10_eps_basic": dict(env=2, agent=0, selector=0, policy=0, target=1, planning=10),
+    "d_taxi_dyna2_sarsa_lambda_ucb_double": dict(env=3, agent=1, selector=1, policy=1, target=0, planning=2),
 }
 N_AGENTS, N_EPISODES, EVAL_AT, FIRST_AGENT = 16, 30, 10, 1000
 
 
 def run_case(c):
-    h = P.hyper(N_EPISODES)
+    h = P.hyper(N_EPISODES, planning_steps=c.get("planning", 0))
     return O.batch_train(P.oracle_config(c, h), FIRST_AGENT, N_AGENTS, N_EPISODES, EVAL_AT, n_threads=4)
 
 

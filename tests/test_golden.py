@@ -45,5 +45,5 @@ def test_oracle_reproduces_golden(key):
 @pytest.mark.parametrize("key", KEYS)
 def test_engine_reproduces_golden(key):
     c = case_of(key)
-    res = P.gpu_run(c, P.hyper(G.N_EPISODES), G.N_AGENTS, G.N_EPISODES, G.EVAL_AT, first_agent_id=G.FIRST_AGENT)
+    res = P.gpu_run(c, P.hyper(G.N_EPISODES, planning_steps=c.get("planning", 0)), G.N_AGENTS, G.N_EPISODES, G.EVAL_AT, first_agent_id=G.FIRST_AGENT)
     check(key, res)
