@@ -250,7 +250,7 @@ __global__ void k_fill(V* ptr, uint64_t n, V value) {
     for (; i < n; i += stride) ptr[i] = value;
 }
 
-// padded device layout [N][S][T][APAD] <-> ABI layout [N][T][S][A]
+// padded device layout [N][row_of(S)][T][APAD] <-> ABI layout [N][T][S][A]
 template <typename V>
 __global__ void k_pack_q(const V* padded, V* packed, uint64_t n_agents, uint32_t S, uint32_t T, uint32_t A, uint32_t APAD) {
     uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,7 +262,7 @@ __global__ void k_pack_q(const V* padded, V* packed, uint64_t n_agents, uint32_t
         uint32_t s = r % S; r /= S;
         uint32_t t = r % T;
         uint64_t n = r / T;
-        packed[idx] = padded[((n * S + s) * T + t) * APAD + a];
+        packed[idx] = padded[((n * S + row_of_rt(A, s)) * T + t) * APAD + a];
     }
 }
 template <typename V>
@@ -276,7 +276,7 @@ __global__ void k_unpack_q(V* padded, const V* packed, uint64_t n_agents, uint32
         uint32_t s = r % S; r /= S;
         uint32_t t = r % T;
         uint64_t n = r / T;
-        padded[((n * S + s) * T + t) * APAD + a] = packed[idx];
+        padded[((n * S + row_of_rt(A, s)) * T + t) * APAD + a] = packed[idx];
     }
 }
 
