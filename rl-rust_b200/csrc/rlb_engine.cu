@@ -420,7 +420,7 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     DevParams& p = e->dp;
     p.q = e->d_q; p.counts = nullptr; p.etr = e->d_etr; p.etr_il = nullptr; p.vis = e->d_vis; p.nvis = e->d_nvis;
     p.rng_n = e->d_rng_n; p.eps = e->d_eps; p.ucb_t = e->d_ucb_t; p.flag = e->d_flag; p.env = e->d_env;
-    p.trans = e->d_trans; p.thr = e->d_thr; p.thr_state = e->d_thr_state; p.n_thr = (uint32_t)e->tables.thr.size();
+    p.trans = e->d_trans; p.thr = e->d_thr; p.thr_state = e->d_thr_state; p.n_thr = (uint32_t)e->tables.thr.size(); p.thr_direct = e->tables.thr_direct;
     p.slip_thr0 = e->tables.slip_thr0; p.slip_thr1 = e->tables.slip_thr1; p.slippery = cfg->slippery;
     p.lr = cfg->learning_rate; p.gamma = cfg->discount_factor; p.lambda = cfg->lambda_factor;
     p.eps0 = cfg->initial_epsilon; p.eps_decay = cfg->epsilon_decay; p.eps_final = cfg->final_epsilon;

@@ -2,6 +2,7 @@
 // engine from the reference constructors' rules and uploaded to the device), the
 // host-callable RNG contract, and the Blackjack observation-id bijection.
 #include "rlb_host.h"
+#include "rlb_taxi_start.h"
 
 #include <cmath>
 #include <cstring>
@@ -73,6 +74,27 @@ static void build_taxi(EnvTables& t) {
             t.thr_state.push_back((uint16_t)state);
         }
     }
+    t.thr_direct = start_index_is_direct(t.thr) ? 1u : 0u;
+}
+
+// Licence for start_index_direct() (rlb_taxi_start.h): compare it with the search at every breakpoint of either step
+// function — each threshold and each k where floor(k * n / 2^52) steps, +-2 — and at both ends.  Between two
+// consecutive breakpoints both functions are constant, so agreement there is agreement everywhere.
+bool start_index_is_direct(const std::vector<uint64_t>& thr) {
+    const uint64_t n = thr.size(), top = 1ull << 52;
+    if (n == 0 || n > 0xffffu) return false;
+    for (uint64_t i = 0; i + 1 < n; ++i) if (!(thr[i] < thr[i + 1])) return false;
+    if (thr[n - 1] > top) return false;
+    auto same = [&](uint64_t k) {
+        if (k >= top) return true;   // also catches the wrap of `x - 2` below 0
+        return start_index_direct(thr.data(), (uint32_t)n, k) == start_index_search(thr.data(), (uint32_t)n, k);
+    };
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t b = (uint64_t)((((unsigned __int128)(i + 1)) << 52) / n);   // around where the guess steps to i + 1
+        for (uint64_t d = 0; d < 5; ++d)
+            if (!same(thr[i] + d - 2) || !same(b + d - 2)) return false;
+    }
+    return same(0) && same(1) && same(top - 1) && same(top - 2);
 }
 
 // env/cliff_walking.rs:22-63.  Reward codes: 0 -> -1, 1 -> -100.
