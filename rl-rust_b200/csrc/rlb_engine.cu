@@ -378,7 +378,7 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     if (!build_env_tables(e->cfg, e->tables, err)) { set_error("%s", err.c_str()); delete e; return RLB_ERR_INVALID_ARG; }
     e->S = e->tables.S;
     e->A = e->tables.A;
-    e->APAD = e->A == 6 ? 8 : e->A;
+    e->APAD = e->A == 6 ? RLB_TAXI_APAD : e->A;   // EnvDims<ENV>::APAD
     e->T = cfg->policy_kind == RLB_POLICY_DOUBLE ? 2 : 1;
     e->real_size = cfg->real_kind == RLB_REAL_F32 ? 4 : 8;
     e->variant = Variant{cfg->real_kind, cfg->policy_kind, cfg->selector_kind, cfg->agent_kind == RLB_AGENT_TRACES ? 1 : 0};
@@ -430,6 +430,10 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     p.n_live = e->tables.n_live;
     std::memcpy(p.row_lut, e->tables.row_lut, sizeof p.row_lut);
     p.seed = cfg->seed; p.first_agent = cfg->first_agent_id; p.n_agents = N;
+    for (uint32_t r = 0; r < 10; ++r) {   // Philox4x32-10 key schedule, the same for every block of every agent
+        p.rk[2 * r] = (uint32_t)cfg->seed + r * 0x9E3779B9u;
+        p.rk[2 * r + 1] = (uint32_t)(cfg->seed >> 32) + r * 0xBB67AE85u;
+    }
     p.mode = 0; p.eval_episodes = 100; p.ep0 = p.ep1 = 0; p.eval_at = 1; p.n_eval = 0;
     p.episodes = nullptr; p.traj = nullptr; p.traj_cap = 0; p.traj_count = nullptr;
     p.totals = e->d_totals; p.eval_ret_total = reinterpret_cast<double*>(e->d_totals + 3);

@@ -17,11 +17,11 @@ __global__ void k_env_construct(const DevParams p) {
     es.p_sum = es.d_sum = es.d_first = 0; es.p_ace = es.d_ace = 0; es.pad[0] = es.pad[1] = 0;
     if constexpr (ENV == RLB_ENV_BLACKJACK) {
         Rng rng;
-        rng.init(p.seed, p.first_agent + i, p.rng_n[i]);
+        rng.init(p, p.first_agent + i, p.rng_n[i]);
         EnvRegs<RLB_ENV_BLACKJACK> env;
-        env.deal(rng);
+        env.deal(rng, p);
         env.to_state(es, 0);
-        p.rng_n[i] = rng.n;
+        p.rng_n[i] = rng.n();
     }
     p.env[i] = es;
 }
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128) k_env_reset(const DevParams p, uint32_t* 
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_agents) return;
     Rng rng;
-    rng.init(p.seed, p.first_agent + i, p.rng_n[i]);
+    rng.init(p, p.first_agent + i, p.rng_n[i]);
     EnvState es = p.env[i];
     EnvRegs<ENV> env;
     env.from_state(es);
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128) k_env_reset(const DevParams p, uint32_t* 
     es.pos = o;
     es.ready = 1;
     p.env[i] = es;
-    p.rng_n[i] = rng.n;
+    p.rng_n[i] = rng.n();
     obs_out[i] = o;
 }
 
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) k_env_step(const DevParams p, const uint3
     }
     if (not_ready_out) not_ready_out[i] = 0;
     Rng rng;
-    rng.init(p.seed, p.first_agent + i, p.rng_n[i]);
+    rng.init(p, p.first_agent + i, p.rng_n[i]);
     EnvRegs<ENV> env;
     env.from_state(es);
     uint32_t o;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) k_env_step(const DevParams p, const uint3
     env.to_state(es, truncated ? es.pos : o);
     if (term) es.ready = 0;
     p.env[i] = es;
-    p.rng_n[i] = rng.n;
+    p.rng_n[i] = rng.n();
     obs_out[i] = o;
     reward_out[i] = r;
     term_out[i] = term ? 1 : 0;
@@ -197,9 +197,9 @@ static __global__ void k_model_get_info(const DevParams p, uint32_t A, uint32_t*
     model.load(p, i);
     if (model.len == 0) { atomicOr(any_empty, 1u); return; }
     Rng rng;
-    rng.init(p.seed, p.first_agent + i, p.rng_n[i]);
-    const uint2 info = model.get_info(rng);
-    p.rng_n[i] = rng.n;
+    rng.init(p, p.first_agent + i, p.rng_n[i]);
+    const uint2 info = model.get_info(rng, p);
+    p.rng_n[i] = rng.n();
     const uint32_t key = info.x & 0xffffu;
     s[i] = key / A; a[i] = key % A; s2[i] = info.x >> 16; reward[i] = (double)__uint_as_float(info.y);
 }
