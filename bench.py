@@ -279,7 +279,7 @@ def main():
         e_.set_stream(stream.cuda_stream)
         engines.append(e_)
     eng = engines[0]
-    table_bytes = sum(N * e_.S * e_.T * (8 if e_.A == 6 else e_.A) * real_size for e_ in engines)
+    table_bytes = sum(N * e_.S * e_.T * e_.A * real_size for e_ in engines)   # every env's rows are unpadded (Taxi: 24-byte f32 rows)
 
     sums_dev = [torch.zeros((chunk, 4), dtype=torch.float64, device="cuda") for _ in cells]
     rec_dtype_size = 16 if real == 0 else 32
