@@ -196,6 +196,7 @@ class Engine:
         s, a, t = C.c_uint32(), C.c_uint32(), C.c_uint32()
         check(lib.rlb_engine_dims(self.h, C.byref(s), C.byref(a), C.byref(t)))
         self.S, self.A, self.T, self.N = s.value, a.value, t.value, n_agents
+        self.seed, self.first_agent_id = int(seed), int(first_agent_id)
         self.real = real
         self.rdtype = np.float32 if real == REAL_F32 else np.float64
         self.episode_dtype = EPISODE_F32 if real == REAL_F32 else EPISODE_F64

@@ -18,6 +18,7 @@ as ("sub", k) for `|a| a - k` (bin/taxi.rs:132) or ("mul", k) for `|a| a * k`
 import numpy as np
 
 from . import _abi as abi
+from . import render as _render
 
 # agent.rs:19-45 — the three GetNextQValue functions are passed by name
 sarsa = abi.TARGET_SARSA
@@ -44,23 +45,49 @@ class Env:
     def _cfg(self):
         return {}
 
+    # render() shows what the step-level reset()/step() calls since the last reset() did: the mirror keeps each env's
+    # position from the observations they return (a truncated step answers obs 0 WITHOUT moving, e.g. taxi.rs:148-151).
+    # Engines of more than TRACK_LIMIT agents are not tracked (rendering millions of envs is nobody's use).
+    TRACK_LIMIT = 4096
+
     def bind(self, engine):
         self._engine = engine
+        self._pos = self._nsteps = None
         return self
 
     def reset(self):                # env.rs:23
         if self._engine is None:
             raise RuntimeError("env is not bound to an engine yet (train an agent on it, or call bind())")
-        return self._engine.env_reset()
+        obs = self._engine.env_reset()
+        if self._engine.N <= self.TRACK_LIMIT:
+            self._pos, self._nsteps = obs.astype(np.int64), np.zeros(self._engine.N, np.int64)
+        return obs
 
     def step(self, action):         # env.rs:24 — raises EnvNotReady where the reference returns Err(EnvNotReady)
         if self._engine is None:
             raise RuntimeError("env is not bound to an engine yet")
         a = np.broadcast_to(np.asarray(action, np.uint32), (self._engine.N,))
-        return self._engine.env_step(a)
+        out = self._engine.env_step(a)
+        if self._pos is not None:
+            truncated = self._nsteps >= getattr(self, "max_steps", np.iinfo(np.int64).max)
+            self._pos = np.where(truncated, self._pos, out[0].astype(np.int64))
+            self._nsteps = self._nsteps + (~truncated)
+        return out
 
     def get_action_label(self, action):   # env.rs:48
         return self.ACTIONS[action]
+
+    def render(self, agent=0):      # env.rs:47 — of ONE of the batched envs (the reference has one)
+        """The reference's `render()` string for agent `agent`'s env, from the state the engine holds."""
+        if self._engine is None:
+            raise RuntimeError("env is not bound to an engine yet")
+        if self._pos is None:
+            raise RuntimeError("render() follows step-level reset()/step() calls (engines of <= %d agents): call reset() first"
+                               % self.TRACK_LIMIT)
+        return self._render_state(int(self._pos[agent]), agent)
+
+    def _render_state(self, pos, agent):
+        raise NotImplementedError
 
 
 class BlackJackEnv(Env):
@@ -69,6 +96,52 @@ class BlackJackEnv(Env):
     kind = abi.ENV_BLACKJACK
     COUNT = 2
     ACTIONS = ("HIT", "STICK")
+
+    # The engine keeps of a hand only what the rules read (two sums, the dealer's first card, two ace flags).  The
+    # cards themselves — which only render() shows — are re-derived on the host from the agents' Philox streams: an env
+    # call draws nothing but cards, so the stream words between the positions before and after it ARE its cards
+    # (blackjack.rs:54-56,76).  Tracked for step-level use only (engines of <= TRACK_LIMIT agents).
+    def bind(self, engine):
+        super().bind(engine)
+        self._hands = None
+        return self
+
+    def _cards_between(self, n0, n1, agent):
+        e = self._engine
+        words = abi.rng_words(e.seed, e.first_agent_id + agent, int(n0), int(n1 - n0)) if n1 > n0 else []
+        return _render.cards_from_words(words)
+
+    def reset(self):                # blackjack.rs:105-116: player gets cards 0 and 1, the dealer cards 2 and 3 (:60-66)
+        if self._engine is None or self._engine.N > self.TRACK_LIMIT:
+            self._hands = None
+            return super().reset()
+        n0 = self._engine.states()["rng_n"].copy()
+        obs = super().reset()
+        n1 = self._engine.states()["rng_n"]
+        self._hands = []
+        for i in range(self._engine.N):
+            c = self._cards_between(n0[i], n1[i], i)
+            self._hands.append(([c[0], c[1]], [c[2], c[3]]))
+        return obs
+
+    def step(self, action):         # blackjack.rs:118-163: HIT draws one player card, anything else the dealer's to >= 17
+        if self._engine is None or self._hands is None:
+            return super().step(action)
+        a = np.broadcast_to(np.asarray(action, np.uint32), (self._engine.N,))
+        n0 = self._engine.states()["rng_n"].copy()
+        out = super().step(a)
+        n1 = self._engine.states()["rng_n"]
+        for i in range(self._engine.N):
+            c = self._cards_between(n0[i], n1[i], i)
+            (self._hands[i][0] if a[i] == 0 else self._hands[i][1]).extend(c)
+        return out
+
+    def _render_state(self, pos, agent):   # blackjack.rs:165-184
+        if getattr(self, "_hands", None) is None:
+            raise RuntimeError("BlackJackEnv.render shows the cards dealt by step-level reset()/step() calls since the "
+                               "last reset (engines of <= %d agents); a fused train()/evaluate() keeps only the sums" % self.TRACK_LIMIT)
+        player, dealer = self._hands[agent]
+        return _render.render_blackjack(bool(self._engine.states()["env_ready"][agent]), dealer, player)
 
     @staticmethod
     def obs_id(dense_index):
@@ -102,6 +175,9 @@ class FrozenLakeEnv(Env):
     def _cfg(self):
         return dict(map_id=self.map_id, slippery=self.is_slippery, max_steps=self.max_steps)
 
+    def _render_state(self, pos, agent):   # frozen_lake.rs:136-149
+        return _render.render_frozen_lake(self.MAP_4X4 if self.map_id == 0 else self.MAP_8X8, pos)
+
 
 class CliffWalkingEnv(Env):
     """env/cliff_walking.rs:6-89"""
@@ -115,6 +191,9 @@ class CliffWalkingEnv(Env):
 
     def _cfg(self):
         return dict(max_steps=self.max_steps)
+
+    def _render_state(self, pos, agent):   # cliff_walking.rs:91-102
+        return _render.render_cliff_walking(pos)
 
 
 class TaxiEnv(Env):
@@ -133,6 +212,36 @@ class TaxiEnv(Env):
     @staticmethod
     def decode(i):                  # taxi.rs:44-55
         return (i // 100, (i // 20) % 5, (i // 4) % 5, i % 4)
+
+    def _render_state(self, pos, agent):   # taxi.rs:161-172
+        return _render.render_taxi(pos)
+
+
+def example_episode(env, get_action, out=print):
+    """`Agent::example` (agent.rs:143-163) over a bound env and an agent's `get_action`: the env before each step, the
+    action's label (`{:?}` of a &str: quoted), the step's reward; when the episode ends the last view, the episode's
+    reward and its length.  The draws and UCB counts it consumes are the reference's (it sits between train and evaluate
+    in the bins, bin/taxi.rs:184-186)."""
+    if env._engine is None:
+        raise RuntimeError("env is not bound to an engine yet")
+    if env._engine.N != 1:
+        raise RuntimeError("example() shows the reference's single env: use an engine of one agent")
+
+    def transitions():
+        curr_action = get_action(env.reset())
+        while True:
+            before = env.render(0)
+            next_obs, reward, terminated = env.step(curr_action)
+            shown, done = int(curr_action[0]), bool(terminated[0])
+            curr_action = get_action(next_obs)           # also on the terminal observation (agent.rs:153)
+            yield before, shown, float(reward[0]), done, env.render(0) if done else None
+            if done:
+                return
+
+    lines = _render.example_lines(env.get_action_label, transitions())
+    for ln in lines:
+        out(ln)
+    return lines
 
 
 # --------------------------------------------------------------------------- Policy<T, COUNT>
@@ -268,6 +377,12 @@ class _Agent:
         res = self.engine.train(n_episodes, eval_at, sums=False, episodes=True)
         ep = res["episodes"]
         return (ep["ret"].T.astype(np.float64), ep["length"].T.astype(np.uint64), ep["td_sum"].T.astype(np.float64))
+
+    def example(self, env, out=print):
+        """agent.rs:143-163: one episode through the step-level calls, printing what the reference prints.  Needs an
+        engine of ONE agent (the reference's single env).  Returns the printed lines."""
+        self._bind(env)
+        return example_episode(env, self.get_action, out=out)
 
     def evaluate(self, env, n_episodes):
         """agent.rs:120-141.  Returns (reward_history, episode_length)."""

@@ -6,7 +6,7 @@ defaults (bin/taxi.rs:22-68): two agents (OneStepAgent, ElegibilityTracesAgent) 
 three bootstrap targets = 12 runs, each `train(n, n/10)` -> `evaluate(n)` -> `agent.reset()` (bin/taxi.rs:158-203), the
 env shared and never re-created, Blackjack followed by its win / loss / draw tally (bin/blackjack.rs:179-207).  The
 curves are `moving_average` (utils.rs:78-93, quirk included) of the per-episode MEAN over the batch's agents; they are
-returned / written as JSON — the plotters PNGs (utils.rs:97-157) are out of scope.
+returned / written as JSON and, with `--plots DIR`, drawn as the bins' five PNG charts (charts.py; utils.rs:97-157).
 
 With n_agents = 1 the reward and length curves are the reference's, value for value (same Philox stream).  The
 "Training Error" curve is windowed over episodes (mean TD per step of each episode), not over raw steps as in the
@@ -56,7 +56,7 @@ def make_env(name, **flags):
 
 
 def run_experiment(env_name, *, n_agents=1, seed=0x5EED0001, real="f64", device=0, tally_games=1000000, policy="basic",
-                   verbose=True, **flags):
+                   verbose=True, show_example=False, **flags):
     """Returns {'legends', 'train_rewards', 'train_episodes_length', 'train_errors', 'test_rewards',
     'test_episodes_length', 'seconds', ['blackjack_rates']} — the five chart series of bin/taxi.rs:205-223."""
     f = dict(DEFAULTS)
@@ -106,6 +106,8 @@ def run_experiment(env_name, *, n_agents=1, seed=0x5EED0001, real="f64", device=
                     out["blackjack_rates"].append(rates)
                     if verbose:
                         print("%s has win-rate of %s%%, loss-rate of %s%% and draw-rate %s%%" % ((LEGENDS[i],) + rates))
+                if show_example:                                                                     # bin/taxi.rs:184-186
+                    out.setdefault("examples", []).append(api.example_episode(env, eng.get_action, out=print if verbose else (lambda _: None)))
                 ev = eng.evaluate(n, sums=True)["sums"]                                              # bin/taxi.rs:188
                 out["test_rewards"].append(moving_average(window, ev[:, 1] / n_agents))
                 out["test_episodes_length"].append(moving_average(window, ev[:, 0] / n_agents))
@@ -176,17 +178,17 @@ def main(argv=None):
         ap.add_argument("--" + name, type=float, default=DEFAULTS[name])
     ap.add_argument("--stochastic_env", action="store_true")
     ap.add_argument("--map", default="4x4")
-    ap.add_argument("--show_example", action="store_true", help="accepted for compatibility; rendering is out of scope")
+    ap.add_argument("--show_example", action="store_true", help="print one rendered episode after each training run (needs --n_agents 1)")
     ap.add_argument("--n_agents", type=int, default=1)
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x5EED0001)
     ap.add_argument("--real", choices=["f32", "f64"], default="f64")
     ap.add_argument("--tally_games", type=int, default=1000000)
     ap.add_argument("--out", default=None, help="write the chart series as JSON here")
+    ap.add_argument("--plots", default=None, help="directory for the five PNG charts of the bins (utils.rs:97-157)")
     a = vars(ap.parse_args(argv))
-    env_name, outp = a.pop("env"), a.pop("out")
-    a.pop("show_example")
+    env_name, outp, plots = a.pop("env"), a.pop("out"), a.pop("plots")
     if env_name == "cliffwalking_model":
-        for k in ("tally_games", "stochastic_env", "map"):
+        for k in ("tally_games", "stochastic_env", "map", "show_example"):
             a.pop(k)
         res = run_model_experiment(**a)
     else:
@@ -194,4 +196,7 @@ def main(argv=None):
     if outp:
         with open(outp, "w") as fh:
             json.dump(res, fh)
+    if plots:
+        from . import charts
+        charts.plot_experiment(res, plots)
     return res

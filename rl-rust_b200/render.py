@@ -69,7 +69,7 @@ def rust_debug_f64(x):
     return repr(float(x))
 
 
-def example_lines(render, label, transitions):
+def example_lines(label, transitions):
     """agent.rs:143-163 as a list of printed lines.  `transitions` yields, per step, (render_before, action, reward,
     terminated, render_after_if_terminated)."""
     lines, total, steps = [], 0.0, 0
