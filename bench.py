@@ -238,6 +238,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--store", type=int, default=0, help="table store: 0 auto, 1 HBM, 2 shared memory")
+    ap.add_argument("--cell-streams", type=int, default=8,
+                    help="multi-cell workloads (c5): host threads / CUDA streams the cells' engines are spread over, so that "
+                         "launches too small to fill the GPU overlap (1 = back to back on one stream)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.agents_per_gpu:
@@ -272,12 +275,18 @@ def main():
     # one engine per cell (N agents each on this GPU); every workload but C5 is a single cell
     cells = [dict(w, **c) for c in w["cells"]] if "cells" in w else [w]
     stream = torch.cuda.current_stream()
+    n_groups = max(1, min(args.cell_streams, len(cells))) if len(cells) > 1 else 1
+    group_streams = [stream] if n_groups == 1 else [torch.cuda.Stream() for _ in range(n_groups)]
     engines = []
-    for cell in cells:
+    for ci, cell in enumerate(cells):
         e_ = P.make_engine(combo(cell, real), workload_hyper(cell), N, first_agent_id=sh.shard(rank, N), device=local_rank,
                            store_kind=args.store)
-        e_.set_stream(stream.cuda_stream)
+        e_.set_stream(group_streams[ci % n_groups].cuda_stream)
         engines.append(e_)
+    pool = None
+    if n_groups > 1:   # the C ABI's train call returns when its launch is done: one host thread per stream keeps them all busy
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(n_groups)
     eng = engines[0]
     table_bytes = sum(N * e_.S * e_.T * e_.A * real_size for e_ in engines)   # every env's rows are unpadded (Taxi: 24-byte f32 rows)
 
@@ -286,16 +295,26 @@ def main():
     state = {"k": 0}
     acc = {"train_steps": 0, "eval_steps": 0, "kernel_ms": 0.0, "launches": 0, "trace_rows": 0, "alg_bytes": 0}
 
+    def run_cell(ci, k, c, host_out):
+        e_ = engines[ci]
+        if c == 0 and k > 0:
+            e_.agent_reset()                                    # src/bin/taxi.rs:200
+        if host_out is None:
+            return e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=sums_dev[ci])
+        return e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=host_out[0][ci], episodes_out=host_out[1][ci])
+
     def step(host_out=None, count=True):
         k = state["k"]
         c = k % chunks_per_run
+        if pool is None:
+            results = None
+        else:                                                   # group g drives cells g, g + n_groups, ... in order on its stream
+            def run_group(g):
+                torch.cuda.set_device(local_rank)
+                return [(ci, run_cell(ci, k, c, host_out)) for ci in range(g, len(cells), n_groups)]
+            results = dict(x for grp in pool.map(run_group, range(n_groups)) for x in grp)
         for ci, (cell, e_) in enumerate(zip(cells, engines)):
-            if c == 0 and k > 0:
-                e_.agent_reset()                                # src/bin/taxi.rs:200
-            if host_out is None:
-                r = e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=sums_dev[ci])
-            else:
-                r = e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=host_out[0][ci], episodes_out=host_out[1][ci])
+            r = run_cell(ci, k, c, host_out) if results is None else results[ci]
             if world > 1:                                       # the path's one collective: per-episode metrics to rank 0
                 if host_out is not None:
                     sums_dev[ci].copy_(host_out[0][ci], non_blocking=True)
@@ -374,7 +393,9 @@ def main():
                        "table_store": {1: "hbm", 2: "shared_memory_groups", 3: "hybrid_smem_q_l2_traces"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)],
                        "eval_steps_executed_not_counted": eval_steps, "env_steps_per_s_incl_eval": (train_steps + eval_steps) / (ms_max * 1e-3),
                        "l2": "inputs larger than L2: %.2f GB of per-agent tables per GPU vs 126 MB L2 (no flush needed)" % (table_bytes / 1e9),
-                       "parallelism": "agents sharded by global id, %d per GPU; one NCCL gather of [episodes,4] metrics per step" % N,
+                       "parallelism": "agents sharded by global id, %d per GPU; one NCCL gather of [episodes,4] metrics per step" % N
+                                      + ("; the %d cells' engines spread over %d host threads / CUDA streams (their launches overlap, so "
+                                         "kernel_share_of_step counts concurrent kernels)" % (len(cells), n_groups) if n_groups > 1 else ""),
                        "wall_s": t_wall},
             "clocks": clocks,
             "gpu_launches": int(dev["launches"]),
@@ -398,6 +419,8 @@ def main():
                                     "sample": "%d agents%s x one full %d-episode run (eval_at %d), C++ oracle single thread, %.1f s"
                                               % (cpu_agents, " per cell" if len(cells) > 1 else "", n_ep, eval_at, dt)}
         print(json.dumps(line), flush=True)
+    if pool is not None:
+        pool.shutdown()
     for e_ in engines:
         e_.close()
     if world > 1:

@@ -15,6 +15,9 @@
 // `training_error` is per episode (sum of the episode's TDs) — see rlb_train_out.traj for the per-step stream.
 #pragma once
 #include <cstdint>
+#include <cstdio>
+#include <iostream>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -68,14 +71,37 @@ class Engine {   // RAII over rlb_engine
 };
 
 // ---------------------------------------------------------------------------------- Env<T, COUNT>  (env.rs:19-49)
+// The cursor fix-up every render() of the reference does (e.g. env/taxi.rs:164-168): walk the newline offsets in order
+// and push the cursor one to the right for each one at or before it (the cursor moves while they are walked).
+inline size_t skip_newlines(const std::string& text, size_t pos) {
+    for (size_t i = 0; i < text.size(); ++i)
+        if (text[i] == '\n' && pos >= i) pos += 1;
+    return pos;
+}
+inline std::string join_rows(const std::vector<std::string>& rows) {
+    std::string out;
+    for (size_t i = 0; i < rows.size(); ++i) { if (i) out += '\n'; out += rows[i]; }
+    return out;
+}
+
 class Env {
    public:
+    static constexpr size_t TRACK_LIMIT = 4096;   // render() follows step-level calls of engines up to this many agents
     virtual ~Env() = default;
     virtual size_t action_size() const = 0;                                  // env.rs:20-22
     virtual void describe(rlb_config& cfg) const = 0;
+    virtual const char* get_action_label(size_t action) const = 0;           // env.rs:48
     std::vector<uint32_t> reset() {                                          // env.rs:23
         std::vector<uint32_t> obs(n());
+        const std::vector<uint64_t> n0 = tracking() ? stream_positions() : std::vector<uint64_t>();
         check(rlb_env_reset(bound(), obs.data()));
+        if (tracking()) {
+            pos_.assign(obs.begin(), obs.end());
+            nsteps_.assign(n(), 0);
+            after_reset(n0, stream_positions());
+        } else {
+            pos_.clear();
+        }
         return obs;
     }
     // env.rs:24 — throws EnvNotReady where the reference returns Err(EnvNotReady)
@@ -83,28 +109,101 @@ class Env {
         std::vector<uint32_t> obs(n());
         std::vector<double> reward(n());
         std::vector<uint8_t> terminated(n());
+        const bool track = !pos_.empty();
+        const std::vector<uint64_t> n0 = track ? stream_positions() : std::vector<uint64_t>();
         check(rlb_env_step(bound(), action.data(), obs.data(), reward.data(), terminated.data(), nullptr));
+        if (track) {
+            for (size_t i = 0; i < n(); ++i) {   // a truncated step answers obs 0 WITHOUT moving (e.g. taxi.rs:148-151)
+                if (nsteps_[i] >= step_limit()) continue;
+                pos_[i] = obs[i];
+                nsteps_[i] += 1;
+            }
+            after_step(action, n0, stream_positions());
+        }
         return {obs, reward, terminated};
     }
-    void bind(Engine* e) { engine_ = e; }
+    // env.rs:47 — of ONE of the batched envs, as the step-level reset()/step() calls since the last reset() left it
+    std::string render(size_t agent = 0) const {
+        if (pos_.empty()) throw std::logic_error("render() follows step-level reset()/step() calls: call reset() first");
+        return render_at(pos_.at(agent), agent);
+    }
+    void bind(Engine* e) { engine_ = e; pos_.clear(); }
     Engine* engine() const { return engine_; }
 
+   protected:
+    virtual std::string render_at(uint32_t pos, size_t agent) const = 0;
+    virtual uint64_t step_limit() const { return std::numeric_limits<uint64_t>::max(); }
+    virtual void after_reset(const std::vector<uint64_t>&, const std::vector<uint64_t>&) {}
+    virtual void after_step(const std::vector<uint32_t>&, const std::vector<uint64_t>&, const std::vector<uint64_t>&) {}
+    std::vector<rlb_agent_state> states() const {
+        std::vector<rlb_agent_state> st(n());
+        check(rlb_get_agent_states(bound(), st.data()));
+        return st;
+    }
+    size_t n() const { return engine_ ? (size_t)engine_->config().n_agents : 0; }
+
    private:
+    bool tracking() const { return n() > 0 && n() <= TRACK_LIMIT; }
+    std::vector<uint64_t> stream_positions() const {
+        std::vector<uint64_t> out;
+        for (const rlb_agent_state& s : states()) out.push_back(s.rng_n);
+        return out;
+    }
     rlb_engine* bound() const {
         if (!engine_) throw std::logic_error("env is not bound to an engine yet (train an agent on it first)");
         return engine_->get();
     }
-    size_t n() const { return engine_ ? (size_t)engine_->config().n_agents : 0; }
     Engine* engine_ = nullptr;
+    std::vector<uint32_t> pos_;
+    std::vector<uint64_t> nsteps_;
 };
 
-class BlackJackEnv : public Env {   // env/blackjack.rs:30-163
+class BlackJackEnv : public Env {   // env/blackjack.rs:30-188
    public:
     BlackJackEnv() = default;
     size_t action_size() const override { return 2; }
     void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_BLACKJACK; }
+    const char* get_action_label(size_t a) const override { static const char* k[] = {"HIT", "STICK"}; return k[a]; }   // :44
     static uint64_t obs_id(uint32_t dense) { return rlb_blackjack_obs_id(dense); }   // blackjack.rs:25-27
     static uint32_t dense_index(uint64_t id) { return rlb_blackjack_dense_index(id); }
+
+   protected:
+    // The engine keeps of a hand only what the rules read; the cards — which only render() shows — are re-derived from
+    // the agent's Philox stream: an env call draws nothing but cards, so the words between the stream positions before
+    // and after it, through rand's Uniform<u8>(1..11) (rlb_rng_card), are its cards (blackjack.rs:54-56,60-66,76).
+    std::vector<uint32_t> cards_between(size_t agent, uint64_t n0, uint64_t n1) const {
+        const rlb_config& c = engine()->config();
+        std::vector<uint32_t> cards;
+        uint64_t w = n0;
+        while (w < n1) cards.push_back(rlb_rng_card(c.seed, c.first_agent_id + agent, &w));
+        return cards;
+    }
+    void after_reset(const std::vector<uint64_t>& n0, const std::vector<uint64_t>& n1) override {
+        player_.assign(n(), {});
+        dealer_.assign(n(), {});
+        for (size_t i = 0; i < n(); ++i) {
+            const std::vector<uint32_t> c = cards_between(i, n0[i], n1[i]);
+            player_[i] = {c.at(0), c.at(1)};
+            dealer_[i] = {c.at(2), c.at(3)};
+        }
+    }
+    void after_step(const std::vector<uint32_t>& action, const std::vector<uint64_t>& n0, const std::vector<uint64_t>& n1) override {
+        for (size_t i = 0; i < n(); ++i) {
+            std::vector<uint32_t>& hand = action[i] == 0 ? player_[i] : dealer_[i];   // HIT: the player; else the dealer to >= 17
+            for (uint32_t c : cards_between(i, n0[i], n1[i])) hand.push_back(c);
+        }
+    }
+    std::string render_at(uint32_t, size_t agent) const override {   // blackjack.rs:165-184
+        std::string out = "Dealer: ";
+        if (states().at(agent).env_ready) out += std::to_string(dealer_.at(agent).at(0));
+        else for (uint32_t c : dealer_.at(agent)) out += std::to_string(c) + " ";
+        out += " \nPlayer: ";
+        for (uint32_t c : player_.at(agent)) out += std::to_string(c) + " ";
+        return out;
+    }
+
+   private:
+    std::vector<std::vector<uint32_t>> player_, dealer_;
 };
 class FrozenLakeEnv : public Env {   // env/frozen_lake.rs:12-134
    public:
@@ -112,6 +211,18 @@ class FrozenLakeEnv : public Env {   // env/frozen_lake.rs:12-134
     FrozenLakeEnv(Map map, bool is_slippery, uint32_t max_steps) : map_(map), slippery_(is_slippery), max_steps_(max_steps) {}
     size_t action_size() const override { return 4; }
     void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_FROZEN_LAKE; c.map_id = map_; c.slippery = slippery_; c.max_steps = max_steps_; }
+    const char* get_action_label(size_t a) const override { static const char* k[] = {"LEFT", "DOWN", "RIGHT", "UP"}; return k[a]; }   // :30
+
+   protected:
+    uint64_t step_limit() const override { return max_steps_; }
+    std::string render_at(uint32_t pos, size_t) const override {   // frozen_lake.rs:136-149: every 'S' becomes 'F', then '@'
+        static const std::vector<std::string> m4 = {"SFFF", "FHFH", "FFFH", "HFFG"};
+        static const std::vector<std::string> m8 = {"SFFFFFFF", "FFFFFFFF", "FFFHFFFF", "FFFFFHFF", "FFFHFFFF", "FHHFFFHF", "FHFFHFHF", "FFFHFFFG"};
+        std::string text = join_rows(map_ == MAP_4X4 ? m4 : m8);
+        for (char& ch : text) if (ch == 'S') ch = 'F';
+        text[skip_newlines(text, pos)] = '@';
+        return text;
+    }
 
    private:
     Map map_; bool slippery_; uint32_t max_steps_;
@@ -121,6 +232,16 @@ class CliffWalkingEnv : public Env {   // env/cliff_walking.rs:6-89
     explicit CliffWalkingEnv(uint32_t max_steps) : max_steps_(max_steps) {}
     size_t action_size() const override { return 4; }
     void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_CLIFF_WALKING; c.max_steps = max_steps_; }
+    const char* get_action_label(size_t a) const override { static const char* k[] = {"LEFT", "DOWN", "RIGHT", "UP"}; return k[a]; }   // :19
+
+   protected:
+    uint64_t step_limit() const override { return max_steps_; }
+    std::string render_at(uint32_t pos, size_t) const override {   // cliff_walking.rs:91-102: byte 39 (the start marker) becomes '_', then '@'
+        std::string text = "____________\n____________\n____________\n@!!!!!!!!!!G";   // :20
+        text[39] = '_';
+        text[skip_newlines(text, pos)] = '@';
+        return text;
+    }
 
    private:
     uint32_t max_steps_;
@@ -130,6 +251,20 @@ class TaxiEnv : public Env {   // env/taxi.rs:10-159
     explicit TaxiEnv(uint32_t max_steps) : max_steps_(max_steps) {}
     size_t action_size() const override { return 6; }
     void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_TAXI; c.max_steps = max_steps_; }
+    const char* get_action_label(size_t a) const override {   // :31
+        static const char* k[] = {"DOWN", "UP", "RIGHT", "LEFT", "PICKUP", "DROPOFF"};
+        return k[a];
+    }
+
+   protected:
+    uint64_t step_limit() const override { return max_steps_; }
+    std::string render_at(uint32_t curr_obs, size_t) const override {   // taxi.rs:161-172: 'T' on the taxi's cell
+        static const std::vector<std::string> map = {"+---------+", "|R: | : :G|", "| : | : : |", "| : : : : |", "| | : | : |", "|Y| : |B: |", "+---------+"};   // :21-29
+        const size_t row = curr_obs / 100, col = (curr_obs / 20) % 5;   // decode, :44-55
+        std::string text = join_rows(map);
+        text[skip_newlines(text, 11 * (row + 1) + 2 * col + 1)] = 'T';   // from_2d_to_1d(11, row + 1, 2 * col + 1), utils.rs:45-47
+        return text;
+    }
 
    private:
     uint32_t max_steps_;
@@ -249,6 +384,41 @@ class Agent {
                 else { rew[d] = e32[src].ret; len[d] = e32[src].length; }
             }
         return r;
+    }
+    // agent.rs:143-163 — one episode through the step-level calls, printing what the reference prints: the env before
+    // each step, the action's label (`{:?}` of a &str: quoted), the step's reward; at the end the last view, the
+    // episode's reward and its length.  Needs an engine of ONE agent (the reference's single env).  Returns the lines.
+    std::vector<std::string> example(Env& env, std::ostream& os = std::cout) {
+        bind(env);
+        if (cfg_.n_agents != 1) throw std::logic_error("example() shows the reference's single env: use an engine of one agent");
+        auto f64_debug = [](double x) {   // `{:?}` of the f64 values an episode produces (integers: "-1.0", "20.0")
+            char buf[64];
+            if (x == (double)(long long)x && x > -1e15 && x < 1e15) std::snprintf(buf, sizeof buf, "%lld.0", (long long)x);
+            else std::snprintf(buf, sizeof buf, "%.17g", x);
+            return std::string(buf);
+        };
+        std::vector<std::string> lines;
+        double epi_reward = 0.0;
+        std::vector<uint32_t> curr_action = get_action(env.reset());
+        int steps = 0;
+        for (;;) {
+            steps += 1;
+            lines.push_back(env.render());
+            auto [next_obs, reward, terminated] = env.step(curr_action);
+            const std::vector<uint32_t> next_action = get_action(next_obs);   // also on the terminal observation (:153)
+            lines.push_back(std::string("\"") + env.get_action_label(curr_action[0]) + "\"");
+            lines.push_back("step reward " + f64_debug(reward[0]));
+            curr_action = next_action;
+            epi_reward += reward[0];
+            if (terminated[0]) {
+                lines.push_back(env.render());
+                lines.push_back("episode reward " + f64_debug(epi_reward));
+                lines.push_back("terminated with " + std::to_string(steps) + " steps");
+                break;
+            }
+        }
+        for (const std::string& l : lines) os << l << "\n";
+        return lines;
     }
     const rlb_train_out& last_train() const { return last_; }   // step totals, kernel time of the last train()
     Engine* engine() const { return engine_; }

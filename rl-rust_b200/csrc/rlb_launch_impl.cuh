@@ -29,6 +29,25 @@ namespace rlb {
 constexpr int kBlock = 128;
 static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
+// HBM-store kernels read their Q rows through L1: ask for no more shared memory per SM than the resident CTAs use (the
+// env table each, + 1 KB the system reserves per CTA), so that the rest of the 256 KB stays L1.  A hint; errors ignored.
+#ifndef RLB_L1_CARVEOUT
+#define RLB_L1_CARVEOUT 1
+#endif
+template <class K>
+inline void prefer_l1(K kern, size_t smem) {
+#if RLB_L1_CARVEOUT
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, kBlock, smem) != cudaSuccess || blocks <= 0) { (void)cudaGetLastError(); return; }
+    const size_t need = (size_t)blocks * (smem + 1024);
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) (void)cudaGetLastError();
+#else
+    (void)kern; (void)smem;
+#endif
+}
+
 // shared-memory (thread-group) table store: compiled for the 4-action envs, whose whole per-agent working set is small
 template <int ENV> struct SmemCapable { static constexpr bool value = (ENV == RLB_ENV_FROZEN_LAKE || ENV == RLB_ENV_CLIFF_WALKING); };
 
@@ -90,7 +109,12 @@ cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStre
     }
     const unsigned grid = grid_for(p.n_agents);
     const size_t smem = EnvTab<ENV>::smem_bytes(p.S);
-#define RLB_CALL(R, P, SL, T) k_run<ENV, R, P, SL, T, STORE_GLOBAL><<<grid, kBlock, smem, stream>>>(p)
+#define RLB_CALL(R, P, SL, T)                                                   \
+    {                                                                           \
+        auto kern = k_run<ENV, R, P, SL, T, STORE_GLOBAL>;                      \
+        prefer_l1(kern, smem);                                                  \
+        kern<<<grid, kBlock, smem, stream>>>(p);                                \
+    }
     RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
     return cudaGetLastError();

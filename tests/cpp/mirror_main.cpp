@@ -3,6 +3,7 @@
 #include <cinttypes>
 #include <cstdio>
 #include <cstring>
+#include <sstream>
 
 #include "rlb.hpp"
 
@@ -85,6 +86,29 @@ int main(int argc, char** argv) {
         auto [r5, l5, e5] = other.train(cliff, 5, 5);                                      // the borrow has ended: plain Q-learning again
         dump("C.after", l5);
         try { model.reset(); std::printf("C no-throw\n"); } catch (const std::logic_error&) { std::printf("C model unbound -> logic_error\n"); }
+
+        // --- Agent::example / Env::render (agent.rs:143-163): one untrained episode per env, seed 0xE8A3, one agent each.
+        // Every transcript line goes out as "D.<env>|<line with newlines as \n>".
+        {
+            Batch b4;
+            b4.seed = 0xE8A3;
+            UniformEpsilonGreed eg4(1.0, Decay::sub(1.0 / 15.0), 0.0);
+            std::ostringstream sink;
+            auto show = [&](const char* tag, Env& e) {
+                OneStepAgent a(policy, 0.95, eg4, qlearning, b4);
+                for (const std::string& line : a.example(e, sink)) {
+                    std::string flat;
+                    for (char ch : line) { if (ch == '\n') flat += "\\n"; else flat += ch; }
+                    std::printf("D.%s|%s\n", tag, flat.c_str());
+                }
+            };
+            TaxiEnv e1(100);
+            FrozenLakeEnv e2_(FrozenLakeEnv::MAP_8X8, true, 100);
+            CliffWalkingEnv e3_(100);
+            BlackJackEnv e4_;
+            show("taxi", e1); show("frozen_lake", e2_); show("cliff_walking", e3_); show("blackjack", e4_);
+            try { other.example(cliff, sink); std::printf("D no-throw\n"); } catch (const std::logic_error&) { std::printf("D example with 2 agents -> logic_error\n"); }
+        }
     } catch (const std::exception& e) {
         std::printf("FAILED: %s\n", e.what());
         return 1;

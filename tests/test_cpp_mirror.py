@@ -86,3 +86,27 @@ def test_mirror_results_equal_oracle():
         r, l, t, _ = s.train(5, 5)
         assert np.array_equal(after[i], l)
         s.close()
+    # D: Agent::example / Env::render through the C++ mirror equal the transcript built from the oracle (the same helper
+    # the Python mirror's test uses) — four envs, one untrained episode each
+    import importlib
+    from test_gpu_example import oracle_transcript, SEED
+    R = importlib.import_module("rl-rust_b200.render")
+    rlb = importlib.import_module("rl-rust_b200")
+    assert "D example with 2 agents -> logic_error" in out
+    decay = 1.0 / 15.0
+    m8 = rlb.FrozenLakeEnv.MAP_8X8
+
+    def hands(n0, n1):
+        return R.cards_from_words(rlb.abi.rng_words(SEED, 0, n0, n1 - n0))
+    cases = {"taxi": (O.ENV_TAXI, {}, lambda pos, ready: R.render_taxi(pos), rlb.TaxiEnv.ACTIONS, None),
+             "frozen_lake": (O.ENV_FROZEN_LAKE, dict(map_id=1, slippery=True), lambda pos, ready: R.render_frozen_lake(m8, pos),
+                             rlb.FrozenLakeEnv.ACTIONS, None),
+             "cliff_walking": (O.ENV_CLIFF_WALKING, {}, lambda pos, ready: R.render_cliff_walking(pos), rlb.CliffWalkingEnv.ACTIONS, None),
+             "blackjack": (O.ENV_BLACKJACK, {}, lambda pos, ready, dealer, player: R.render_blackjack(ready, dealer, player),
+                           rlb.BlackJackEnv.ACTIONS, hands)}
+    for tag, (kind, extra, view, labels, hd) in cases.items():
+        got = [l.split("|", 1)[1].replace("\\n", "\n") for l in out.splitlines() if l.startswith("D.%s|" % tag)]
+        cfg = O.make_config(kind, target=O.TARGET_QLEARNING, eps_decay=decay, seed=SEED, **extra)
+        want = oracle_transcript(cfg, kind, view, lambda a, labels=labels: labels[a], hd)
+        assert got == want, tag
+
