@@ -321,7 +321,7 @@ def main():
                 state["curves"] = sh.gather_episode_sums(sums_dev[ci])   # [world, chunk, 4] on rank 0
             if count:
                 acc["train_steps"] += r["train_steps"]; acc["eval_steps"] += r["eval_steps"]
-                acc["kernel_ms"] += r["kernel_ms"]; acc["launches"] += r["kernel_launches"] + 1   # + k_episode_sums
+                acc["kernel_ms"] += r["kernel_ms"]; acc["launches"] += 2 * r["kernel_launches"]   # each k_run is followed by one k_episode_sums
                 acc["trace_rows"] += r["trace_rows"]
                 acc["alg_bytes"] += algorithmic_bytes(cell, real_size, r["train_steps"], r["trace_rows"])
         state["k"] = k + 1
