@@ -47,3 +47,34 @@ def test_engine_reproduces_golden(key):
     c = case_of(key)
     res = P.gpu_run(c, P.hyper(G.N_EPISODES, planning_steps=c.get("planning", 0)), G.N_AGENTS, G.N_EPISODES, G.EVAL_AT, first_agent_id=G.FIRST_AGENT)
     check(key, res)
+
+
+# ---- `Agent::example` transcripts (tests/golden/example_v1.json, made by tests/golden/make_example_golden.py)
+import json   # noqa: E402
+
+import make_example_golden as GE   # noqa: E402
+
+EXAMPLES = json.load(open(os.path.join(HERE, "golden", "example_v1.json")))
+
+
+def test_oracle_reproduces_golden_example_transcripts():
+    got = GE.transcripts()
+    assert sorted(got) == sorted(EXAMPLES)
+    for name in EXAMPLES:
+        assert got[name] == EXAMPLES[name], name
+    # what the four episodes must show whatever the stream: Taxi's random walk is truncated after max_steps + 1 steps
+    # WITHOUT moving the taxi (taxi.rs:148-151), CliffWalking's fall costs -100 and ends the episode (cliff_walking.rs:26-28)
+    assert EXAMPLES["taxi"][-1] == "terminated with 101 steps" and EXAMPLES["taxi"][-4] == "step reward 0.0"
+    assert EXAMPLES["taxi"][-3] == EXAMPLES["taxi"][-6]            # the view after the truncated step == the view before it
+    assert EXAMPLES["cliff_walking"][-2] == "episode reward -101.0"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(EXAMPLES))
+def test_engine_reproduces_golden_example_transcripts(rlb, name):
+    """The mirror's example() on the GPU against the committed transcript, no oracle in the loop."""
+    sel = rlb.UniformEpsilonGreed(1.0, ("sub", GE.DECAY), 0.0)
+    agent = rlb.OneStepAgent(rlb.TabularPolicy(0.05, 0.0), 0.95, sel, rlb.qlearning, n_agents=1, seed=GE.SEED, real="f64")
+    env = {"taxi": lambda: rlb.TaxiEnv(100), "frozen_lake": lambda: rlb.FrozenLakeEnv(rlb.FrozenLakeEnv.MAP_8X8, True, 100),
+           "cliff_walking": lambda: rlb.CliffWalkingEnv(100), "blackjack": rlb.BlackJackEnv}[name]()
+    assert agent.example(env, out=lambda _: None) == EXAMPLES[name]
