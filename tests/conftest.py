@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build them once, as the driver's build() does
+    if not os.path.exists(os.path.join(ROOT, "rl-rust_b200", "librlb.so")) or not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
