@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RLB_ABI_VERSION 1
+#define RLB_ABI_VERSION 2
 
 typedef struct rlb_engine rlb_engine;
 
@@ -46,7 +46,8 @@ typedef enum rlb_status {
     RLB_ERR_INVALID_ARG = 2,   /* includes eval_at == 0 (agent.rs:107 divides by it) */
     RLB_ERR_CUDA = 3,
     RLB_ERR_OOM = 4,
-    RLB_ERR_UNSUPPORTED = 5
+    RLB_ERR_UNSUPPORTED = 5,
+    RLB_ERR_NCCL = 6           /* a NCCL call failed, or libnccl.so.2 could not be loaded (rlb_comm_*) */
 } rlb_status;
 
 typedef enum rlb_env_kind {      /* env.rs:9-14 */
@@ -125,7 +126,17 @@ typedef struct rlb_config {
                                     4-lane thread group), 3 = hybrid (Q in shared memory, eligibility rows streamed through L2) */
     uint32_t planning_steps;     /* > 0: the agent is wrapped as InternalModelAgent::new(agent, RandomModel::default(), planning_steps)
                                     (agent/internal_model_agent.rs:17-29; bin/cliffwalking_model.rs:150-156 passes 10).  Needs the HBM store. */
+    /* FrozenLakeEnv::new(map: &[&str], ..) (frozen_lake.rs:48) with a caller-supplied map: map_id = RLB_MAP_CUSTOM and
+     * `map` = the rows joined without separators (map_rows * map_cols chars of 'S' 'F' 'H' 'G', row-major; read during
+     * rlb_engine_create only).  Every 'S' cell is a start cell: reset() draws among them with `categorical_sample` over
+     * the 1/count distribution (:54-66,106-109); a map without 'S' starts at cell 0, as the reference's all-zero
+     * distribution does.  At most 1024 cells. */
+    uint32_t map_rows, map_cols;
+    const char* map;
 } rlb_config;
+#define RLB_MAP_4X4 0
+#define RLB_MAP_8X8 1
+#define RLB_MAP_CUSTOM 2
 
 /* Per-training-episode record streamed by the fused kernel (agent.rs:72-75,98,103,115):
  * episode length, episode return, and the episode's sum / sum of |.| of the per-step
@@ -166,6 +177,14 @@ typedef struct rlb_train_out {
     float kernel_ms;             /* out: device time of the fused kernel launches (CUDA events) */
     uint32_t kernel_launches;    /* out */
     uint64_t trace_rows;         /* out: eligibility rows swept (elegibility_traces_agent.rs:86), for the roofline */
+    /* `training_error` (agent.rs:73,98,117): the temporal difference of EVERY training step, in step order, episodes
+     * concatenated — [n_agents][td_capacity] Real; td_count [n_agents] u64 receives the number of training steps each
+     * agent took in this call (the first min(count, capacity) values are stored).  Optional (NULL / 0): at scale the
+     * per-episode td_sum / td_abs_sum of the episode records are the stream; this is the exact per-step vector the
+     * bins window for their "Training Error" chart (bin/taxi.rs:170-174).  Host or device buffers. */
+    void* td_steps;
+    uint64_t td_capacity;
+    uint64_t* td_count;
 } rlb_train_out;
 
 /* Complete per-agent resumable state besides the tables. */
@@ -240,6 +259,25 @@ rlb_status rlb_agent_train(rlb_engine* e, uint64_t n_episodes, uint64_t eval_at,
 /* Episodes [ep_begin, ep_end) of the same train() call, so a run can be driven in chunks
  * (outputs are indexed from ep_begin). */
 rlb_status rlb_agent_train_range(rlb_engine* e, uint64_t ep_begin, uint64_t ep_end, uint64_t eval_at, rlb_train_out* out);
+/* The same call without the final wait: everything (kernels, the reduction, the device->host copies of records and
+ * sums) is enqueued on the engine's streams and the call returns.  The buffers named in `out` — and `out` itself —
+ * must stay valid until rlb_agent_train_wait(), which blocks until the work is done and fills out's scalar fields
+ * (train_steps ... trace_rows).  One call may be pending per engine; any other compute call on the engine waits for it
+ * first.  This is how a host thread keeps several engines (the cells of a sweep, bin/taxi.rs:158-203, or the GPUs of a
+ * box) busy at once, and how the record copy of call i hides behind the kernels of call i + 1.  Host record / td
+ * buffers should be pinned (cudaHostAlloc / cudaHostRegister) for the copies to be asynchronous. */
+rlb_status rlb_agent_train_range_async(rlb_engine* e, uint64_t ep_begin, uint64_t ep_end, uint64_t eval_at, rlb_train_out* out);
+rlb_status rlb_agent_train_wait(rlb_engine* e);
+/* One iteration of the loop at agent.rs:83-106 for every agent, fused into ONE launch: an agent whose episode is over
+ * (or not begun) does `curr_obs = env.reset(); curr_action = get_action(curr_obs)` (agent.rs:83-84; kind 0), any other
+ * agent does `env.step(curr_action)`, `get_action(next_obs)`, `update(..)` and the bookkeeping of :88-105 (kind 1), the
+ * engine keeping curr_obs / curr_action on the device.  A host loop over this call reproduces rlb_agent_train's
+ * trajectory (without the injected evaluate); it is the low-latency form of the three step-level calls
+ * rlb_env_step + rlb_agent_get_action + rlb_agent_update for trait-object style drivers.  Outputs [N], any may be
+ * NULL: kind u8, obs u32 (the observation returned by reset / step), action u32 (chosen on it), reward f64,
+ * terminated u8, td Real. */
+rlb_status rlb_agent_step(rlb_engine* e, uint8_t* kind_out, uint32_t* obs_out, uint32_t* action_out, double* reward_out,
+                          uint8_t* terminated_out, void* td_out);
 /* Agent::evaluate (agent.rs:120-141).  episodes_out: [n_episodes][N] episode records
  * (td fields zero); sums_out [n_episodes][4] as in rlb_train_out.  Either may be NULL. */
 rlb_status rlb_agent_evaluate(rlb_engine* e, uint64_t n_episodes, void* episodes_out, double* sums_out,
@@ -288,6 +326,37 @@ rlb_status rlb_download_tables(rlb_engine* e, void* q_out, uint32_t* counts_out)
 rlb_status rlb_upload_tables(rlb_engine* e, const void* q, const uint32_t* counts);
 rlb_status rlb_get_agent_states(rlb_engine* e, rlb_agent_state* states_out /* [N] */);
 rlb_status rlb_set_agent_states(rlb_engine* e, const rlb_agent_state* states /* [N] */);
+
+/* ---- multi-GPU: the path's one exchange (no reference equivalent: the crate is single-threaded) ----------------
+ * Agents are independent, so a job shards by contiguous ranges of GLOBAL agent id (rlb_config.first_agent_id) with no
+ * data-path collective.  The only exchange is one gather per run (or per chunk) of the per-episode metric sums —
+ * rlb_train_out.episode_sums, [n_episodes][4] f64 per engine — to the root rank for the training charts
+ * (bin/taxi.rs:170-223), done here with grouped ncclSend / ncclRecv over NVLink (libnccl.so.2 is loaded on first use;
+ * the system library 2.27 has no ncclGather).  Two ways to build the communicator:
+ *   - one process per GPU (torchrun, MPI, a Rust launcher ...): rank 0 calls rlb_comm_unique_id(), the host side
+ *     passes the 128 bytes to the other ranks by any means, every rank calls rlb_comm_init_rank();
+ *   - one process driving several GPUs (one engine per device, e.g. from Rust threads): rlb_comm_init_all().
+ * NCCL failures return RLB_ERR_NCCL with the NCCL error string in rlb_last_error_string(). */
+typedef struct rlb_comm rlb_comm;
+#define RLB_COMM_ID_BYTES 128
+rlb_status rlb_comm_unique_id(uint8_t id_out[RLB_COMM_ID_BYTES]);
+rlb_status rlb_comm_init_rank(const uint8_t id[RLB_COMM_ID_BYTES], int32_t world_size, int32_t rank, int32_t device, rlb_comm** out);
+/* comms_out [n_devices]: one communicator per listed device, ranks 0 .. n_devices-1 in list order */
+rlb_status rlb_comm_init_all(const int32_t* devices, int32_t n_devices, rlb_comm** comms_out);
+void rlb_comm_destroy(rlb_comm* c);
+int32_t rlb_comm_rank(const rlb_comm* c);
+int32_t rlb_comm_world_size(const rlb_comm* c);
+/* Every rank contributes local_sums [n_episodes][4] f64; rank `root` receives gathered_out [world][n_episodes][4]
+ * (ignored elsewhere; may be NULL there).  DEVICE buffers, enqueued on `cuda_stream` (cudaStream_t as void*, NULL =
+ * the communicator's own stream, synchronised before returning).  With rlb_comm_init_all the calls of the
+ * communicators must be issued between rlb_comm_group_begin / rlb_comm_group_end or from one thread per rank. */
+rlb_status rlb_comm_gather_episode_sums(rlb_comm* c, const double* local_sums, uint64_t n_episodes, double* gathered_out,
+                                        int32_t root, void* cuda_stream);
+/* sum over ranks of `count` f64 values, in place, on every rank (job totals: steps, max-reduced times travel as sums
+ * of one-hot vectors).  DEVICE buffer. */
+rlb_status rlb_comm_allreduce_sum(rlb_comm* c, double* values, uint64_t count, void* cuda_stream);
+rlb_status rlb_comm_group_begin(void);
+rlb_status rlb_comm_group_end(void);
 
 /* ---- RNG injection contract, host-callable (no device needed) -------------------------------
  * Replaces rand::thread_rng() at blackjack.rs:54,76; taxi.rs:136-137; frozen_lake.rs:107-108,126;

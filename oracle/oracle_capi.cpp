@@ -28,6 +28,10 @@ struct OracleConfig {
     uint64_t seed;
     uint32_t planning_steps; // > 0: the agent is wrapped in InternalModelAgent(RandomModel, planning_steps)
     uint32_t pad;
+    // frozen_lake with map_id == 2: FrozenLakeEnv::new(map, ..) on the caller's own rows (frozen_lake.rs:48), joined
+    // without separators, map_rows * map_cols cells
+    uint32_t map_rows, map_cols;
+    const char* map;
 };
 
 struct OracleState {
@@ -250,8 +254,12 @@ SessionBase* make_session(const OracleConfig& c, u64 agent_id) {
         }
         case 1: {
             auto* s = new Session<4, Real>(c, agent_id, nullptr);
-            s->env.reset(new FrozenLakeEnv(c.map_id == 0 ? FrozenLakeEnv::map_4x4() : FrozenLakeEnv::map_8x8(),
-                                           c.slippery != 0, c.max_steps, &s->rng));
+            std::vector<std::string> map = c.map_id == 0 ? FrozenLakeEnv::map_4x4() : FrozenLakeEnv::map_8x8();
+            if (c.map_id == 2) {
+                map.clear();
+                for (uint32_t r = 0; r < c.map_rows; ++r) map.emplace_back(c.map + (size_t)r * c.map_cols, c.map_cols);
+            }
+            s->env.reset(new FrozenLakeEnv(map, c.slippery != 0, c.max_steps, &s->rng));
             s->finish_init();
             return s;
         }

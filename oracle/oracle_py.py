@@ -29,6 +29,7 @@ class OracleConfig(C.Structure):
         ("lr", C.c_double), ("gamma", C.c_double), ("lambda_", C.c_double), ("eps0", C.c_double),
         ("eps_decay", C.c_double), ("eps_final", C.c_double), ("ucb_c", C.c_double), ("default_q", C.c_double),
         ("seed", C.c_uint64), ("planning_steps", C.c_uint32), ("pad", C.c_uint32),
+        ("map_rows", C.c_uint32), ("map_cols", C.c_uint32), ("map", C.c_char_p),
     ]
 
 
@@ -138,11 +139,15 @@ def env_dims(cfg):
 def make_config(env_kind, *, map_id=1, slippery=0, max_steps=100, policy=POLICY_BASIC, selector=SEL_EPS_GREEDY,
                 target=TARGET_QLEARNING, agent=AGENT_ONE_STEP, real=REAL_F64, decay_kind=DECAY_SUB, lr=0.05,
                 gamma=0.95, lambda_=0.5, eps0=1.0, eps_decay=2e-5, eps_final=0.0, ucb_c=0.5, default_q=0.0,
-                seed=0x5EED0001, planning_steps=0):
-    """Defaults = the reference CLI's (bin/taxi.rs:22-68) with n_episodes=100000 -> decay 2e-5."""
+                seed=0x5EED0001, planning_steps=0, map_rows=None):
+    """Defaults = the reference CLI's (bin/taxi.rs:22-68) with n_episodes=100000 -> decay 2e-5.
+    map_rows: a caller-supplied FrozenLake map (list of equally long S/F/H/G strings, frozen_lake.rs:48)."""
+    rows, cols, flat = 0, 0, None
+    if map_rows is not None:
+        rows, cols, flat, map_id = len(map_rows), len(map_rows[0]), "".join(map_rows).encode("ascii"), 2
     return OracleConfig(env_kind, map_id, int(slippery), max_steps, policy, selector, target, agent, real,
                         decay_kind, lr, gamma, lambda_, eps0, eps_decay, eps_final, ucb_c, default_q, seed,
-                        planning_steps, 0)
+                        planning_steps, 0, rows, cols, flat)
 
 
 class Session:

@@ -13,7 +13,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RLB_LIB", os.path.join(_HERE, "librlb.so"))   # RLB_LIB: A/B a differently built library
 
-OK, ERR_ENV_NOT_READY, ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED = range(6)
+OK, ERR_ENV_NOT_READY, ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_UNSUPPORTED, ERR_NCCL = range(7)
+MAP_4X4, MAP_8X8, MAP_CUSTOM = 0, 1, 2
+COMM_ID_BYTES = 128
 ENV_BLACKJACK, ENV_FROZEN_LAKE, ENV_CLIFF_WALKING, ENV_TAXI = range(4)
 POLICY_BASIC, POLICY_DOUBLE = 0, 1
 SEL_EPS_GREEDY, SEL_UCB = 0, 1
@@ -34,6 +36,7 @@ class RlbConfig(C.Structure):
         ("confidence_level", C.c_double), ("default_value", C.c_double),
         ("seed", C.c_uint64), ("n_agents", C.c_uint64), ("first_agent_id", C.c_uint64),
         ("store_kind", C.c_uint32), ("planning_steps", C.c_uint32),
+        ("map_rows", C.c_uint32), ("map_cols", C.c_uint32), ("map", C.c_char_p),
     ]
 
 
@@ -43,6 +46,7 @@ class RlbTrainOut(C.Structure):
         ("traj_count", C.c_void_p), ("train_steps", C.c_uint64), ("eval_steps", C.c_uint64),
         ("eval_return_sum", C.c_double), ("eval_episodes", C.c_uint64), ("kernel_ms", C.c_float),
         ("kernel_launches", C.c_uint32), ("trace_rows", C.c_uint64),
+        ("td_steps", C.c_void_p), ("td_capacity", C.c_uint64), ("td_count", C.c_void_p),
     ]
 
 
@@ -66,6 +70,9 @@ EXPORTS = [
     "rlb_set_agent_states", "rlb_philox4x32_10", "rlb_rng_words", "rlb_rng_uniform_f64", "rlb_rng_uniform_usize",
     "rlb_rng_card", "rlb_rng_gen_range", "rlb_model_add_info", "rlb_model_get_info", "rlb_model_reset", "rlb_model_capacity",
     "rlb_download_model", "rlb_upload_model", "rlb_blackjack_obs_id", "rlb_blackjack_dense_index", "rlb_blackjack_decode",
+    "rlb_agent_train_range_async", "rlb_agent_train_wait", "rlb_agent_step",
+    "rlb_comm_unique_id", "rlb_comm_init_rank", "rlb_comm_init_all", "rlb_comm_destroy", "rlb_comm_rank", "rlb_comm_world_size",
+    "rlb_comm_gather_episode_sums", "rlb_comm_allreduce_sum", "rlb_comm_group_begin", "rlb_comm_group_end",
 ]
 
 
@@ -120,6 +127,22 @@ def _load():
     L.rlb_agent_train.argtypes = [vp, u64, u64, P(RlbTrainOut)]
     L.rlb_agent_train_range.argtypes = [vp, u64, u64, u64, P(RlbTrainOut)]
     L.rlb_agent_evaluate.argtypes = [vp, u64, vp, vp, P(u64)]
+    L.rlb_agent_train_range_async.argtypes = [vp, u64, u64, u64, P(RlbTrainOut)]
+    L.rlb_agent_train_wait.argtypes = [vp]
+    L.rlb_agent_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.rlb_comm_unique_id.argtypes = [vp]
+    L.rlb_comm_init_rank.argtypes = [vp, i32, i32, i32, P(vp)]
+    L.rlb_comm_init_all.argtypes = [P(i32), i32, P(vp)]
+    L.rlb_comm_destroy.restype = None
+    L.rlb_comm_destroy.argtypes = [vp]
+    L.rlb_comm_rank.restype = i32
+    L.rlb_comm_rank.argtypes = [vp]
+    L.rlb_comm_world_size.restype = i32
+    L.rlb_comm_world_size.argtypes = [vp]
+    L.rlb_comm_gather_episode_sums.argtypes = [vp, vp, u64, vp, i32, vp]
+    L.rlb_comm_allreduce_sum.argtypes = [vp, vp, u64, vp]
+    L.rlb_comm_group_begin.argtypes = []
+    L.rlb_comm_group_end.argtypes = []
     L.rlb_policy_predict.argtypes = [vp, vp, vp]
     L.rlb_policy_get_values.argtypes = [vp, vp, vp]
     L.rlb_policy_update.argtypes = [vp, vp, vp, vp, vp]
@@ -186,11 +209,18 @@ class Engine:
                  selector=SEL_EPS_GREEDY, target=TARGET_QLEARNING, agent=AGENT_ONE_STEP, real=REAL_F32,
                  decay_kind=DECAY_SUB, learning_rate=0.05, discount_factor=0.95, lambda_factor=0.5,
                  initial_epsilon=1.0, epsilon_decay=2e-5, final_epsilon=0.0, confidence_level=0.5, default_value=0.0,
-                 seed=0x5EED0001, first_agent_id=0, device=0, store_kind=0, planning_steps=0):
+                 seed=0x5EED0001, first_agent_id=0, device=0, store_kind=0, planning_steps=0, map_rows=None):
+        # map_rows: FrozenLakeEnv::new's `map: &[&str]` (frozen_lake.rs:48) — a list of equally long strings of S/F/H/G
+        rows, cols, flat = 0, 0, None
+        if map_rows is not None:
+            map_rows = [str(r) for r in map_rows]
+            if not map_rows or any(len(r) != len(map_rows[0]) for r in map_rows):
+                raise ValueError("map rows must be non-empty and equally long")
+            rows, cols, flat, map_id = len(map_rows), len(map_rows[0]), "".join(map_rows).encode("ascii"), MAP_CUSTOM
         self.cfg = RlbConfig(C.sizeof(RlbConfig), env_kind, map_id, int(bool(slippery)), max_steps, policy, selector,
                              target, agent, real, decay_kind, device, learning_rate, discount_factor, lambda_factor,
                              initial_epsilon, epsilon_decay, final_epsilon, confidence_level, default_value, seed,
-                             n_agents, first_agent_id, store_kind, planning_steps)
+                             n_agents, first_agent_id, store_kind, planning_steps, rows, cols, flat)
         self.h = C.c_void_p()
         check(lib.rlb_engine_create(C.byref(self.cfg), C.byref(self.h)))
         s, a, t = C.c_uint32(), C.c_uint32(), C.c_uint32()
@@ -228,8 +258,12 @@ class Engine:
 
     # ---- Agent::train / evaluate
     def train(self, n_episodes, eval_at, *, ep_begin=0, sums=True, episodes=False, traj_capacity=0, sums_out=None,
-              episodes_out=None):
-        """Agent::train (agent.rs:66-118), episodes [ep_begin, n_episodes).  Returns a dict."""
+              episodes_out=None, td_capacity=0, wait=True):
+        """Agent::train (agent.rs:66-118), episodes [ep_begin, n_episodes).  Returns a dict.
+        td_capacity > 0 also returns `training_error` (agent.rs:98,117): res["td_steps"] [N, td_capacity] and
+        res["td_count"] [N] (steps taken; the first min(count, capacity) TDs of each agent are stored).
+        wait=False enqueues the call and returns (rlb_agent_train_range_async); the scalar results are filled in
+        by train_wait(), which returns the same dict."""
         n = n_episodes - ep_begin
         out = RlbTrainOut()
         res = {}
@@ -251,11 +285,44 @@ class Engine:
             out.traj = ptr(res["traj"])
             out.traj_capacity = traj_capacity
             out.traj_count = ptr(res["traj_count"])
+        if td_capacity:
+            res["td_steps"] = np.zeros((self.N, td_capacity), self.rdtype)
+            res["td_count"] = np.zeros(self.N, np.uint64)
+            out.td_steps = ptr(res["td_steps"])
+            out.td_capacity = td_capacity
+            out.td_count = ptr(res["td_count"])
+        if not wait:
+            self._pending = getattr(self, "_pending", [])
+            self._pending.append((out, res))       # keeps `out` and the buffers alive until train_wait()
+            check(lib.rlb_agent_train_range_async(self.h, ep_begin, n_episodes, eval_at, C.byref(out)))
+            return res
         check(lib.rlb_agent_train_range(self.h, ep_begin, n_episodes, eval_at, C.byref(out)))
+        self._fill(out, res)
+        return res
+
+    @staticmethod
+    def _fill(out, res):
         res.update(train_steps=out.train_steps, eval_steps=out.eval_steps, eval_return_sum=out.eval_return_sum,
                    eval_episodes=out.eval_episodes, kernel_ms=out.kernel_ms, kernel_launches=out.kernel_launches,
                    trace_rows=out.trace_rows)
-        return res
+
+    def train_wait(self):
+        """rlb_agent_train_wait: complete every train(wait=False) call; returns their result dicts, oldest first."""
+        check(lib.rlb_agent_train_wait(self.h))
+        done = []
+        for out, res in getattr(self, "_pending", []):
+            self._fill(out, res)
+            done.append(res)
+        self._pending = []
+        return done
+
+    def agent_step(self):
+        """rlb_agent_step: one iteration of the loop at agent.rs:83-106 for every agent, one launch."""
+        kind, term = np.zeros(self.N, np.uint8), np.zeros(self.N, np.uint8)
+        obs, act = np.zeros(self.N, np.uint32), np.zeros(self.N, np.uint32)
+        rew, td = np.zeros(self.N, np.float64), np.zeros(self.N, self.rdtype)
+        check(lib.rlb_agent_step(self.h, ptr(kind), ptr(obs), ptr(act), ptr(rew), ptr(term), ptr(td)))
+        return dict(kind=kind, obs=obs, action=act, reward=rew, terminated=term.astype(bool), td=td)
 
     def evaluate(self, n_episodes, *, sums=True, episodes=False):
         """Agent::evaluate (agent.rs:120-141)."""
@@ -434,3 +501,56 @@ def blackjack_obs_id(dense_index):
 
 def blackjack_dense_index(obs_id):
     return lib.rlb_blackjack_dense_index(obs_id)
+
+
+class Comm:
+    """rlb_comm: the path's one multi-GPU exchange (NCCL send/recv gather of the per-episode metric sums)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        check(lib.rlb_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def init_rank(cls, unique_id, world_size, rank, device):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        check(lib.rlb_comm_init_rank(buf, world_size, rank, device, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def init_all(cls, devices):
+        devs = (C.c_int32 * len(devices))(*devices)
+        hs = (C.c_void_p * len(devices))()
+        check(lib.rlb_comm_init_all(devs, len(devices), hs))
+        return [cls(C.c_void_p(h)) for h in hs]
+
+    @property
+    def rank(self):
+        return lib.rlb_comm_rank(self.h)
+
+    @property
+    def world_size(self):
+        return lib.rlb_comm_world_size(self.h)
+
+    def gather_episode_sums(self, local_sums, gathered=None, root=0, stream=None):
+        """local_sums: CUDA f64 [E,4]; gathered: CUDA f64 [world,E,4] on the root."""
+        check(lib.rlb_comm_gather_episode_sums(self.h, ptr(local_sums), local_sums.shape[0], ptr(gathered), root,
+                                               C.c_void_p(stream) if stream else None))
+        return gathered
+
+    def allreduce_sum(self, values, stream=None):
+        check(lib.rlb_comm_allreduce_sum(self.h, ptr(values), values.numel(), C.c_void_p(stream) if stream else None))
+        return values
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.rlb_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

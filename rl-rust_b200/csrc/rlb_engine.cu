@@ -19,17 +19,6 @@ using namespace rlb;
 
 namespace {
 
-thread_local std::string g_last_error;
-
-void set_error(const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    g_last_error = buf;
-}
-
 rlb_status cuda_fail(cudaError_t err, const char* what) {
     set_error("%s: %s", what, cudaGetErrorString(err));
     return err == cudaErrorMemoryAllocation ? RLB_ERR_OOM : RLB_ERR_CUDA;
@@ -85,6 +74,29 @@ struct rlb_engine {
     // done" / "copy done" events
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
+    uint64_t last_pipeline_chunk = 0;  // episodes per scratch half of the last pipelined call
+    uint64_t launch_counter = 0;       // k_run launches writing records for a host buffer, over all calls: picks the scratch half
+    // rlb_agent_step: curr_obs / curr_action of every agent
+    uint32_t* d_cur_obs = nullptr;
+    uint32_t* d_cur_action = nullptr;
+    double* d_log_table = nullptr;     // ln(t) for t < RLB_LOG_TABLE_N (UCB), filled on the device by portable_log
+    // Calls whose work is enqueued but not yet waited for (rlb_agent_train_range_async): at most two, so that the
+    // kernels of call i + 1 are in the queue before the host blocks on the copies of call i.
+    struct Pending {
+        int mode = 0;
+        rlb_train_out* out = nullptr;
+        uint64_t* eval_steps_out = nullptr;
+        std::vector<cudaEvent_t> events;             // (start, stop) per k_run launch
+        cudaEvent_t done = nullptr;                  // after everything the call enqueued on the main stream
+        cudaEvent_t copies_done = nullptr;           // after its last record copy on the copy stream (pipelined calls)
+        unsigned long long* h_totals = nullptr;      // pinned [8]
+        bool pipelined = false;
+        rlb_traj_record* d_traj = nullptr; uint64_t* d_traj_count = nullptr; bool own_traj = false, own_count = false;
+        void* d_td = nullptr; uint64_t* d_td_count = nullptr; bool own_td = false, own_td_count = false;
+    };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> event_pool;             // timing events not in use
+    std::vector<unsigned long long*> totals_pool;    // pinned [8] blocks not in use
 };
 
 namespace {
@@ -102,6 +114,12 @@ cudaError_t copy_out(rlb_engine* e, void* dst, const void* src_dev, size_t bytes
     cudaError_t err = cudaMemcpyAsync(dst, src_dev, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream);
     if (err != cudaSuccess) return err;
     return is_device_ptr(dst) ? cudaSuccess : cudaStreamSynchronize(e->stream);
+}
+
+// the same without waiting: complete once the stream reaches it (immediately for pageable host memory)
+cudaError_t copy_async(rlb_engine* e, void* dst, const void* src_dev, size_t bytes) {
+    if (!dst || !bytes) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src_dev, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream);
 }
 
 // make caller data (host or device) readable on the device; returns a device pointer
@@ -185,7 +203,7 @@ rlb_status pick_store(rlb_engine* e) {
     const size_t per_block_max = 227 * 1024, per_sm = 228 * 1024;
     const size_t b_group = store_bytes(e, STORE_SMEM), b_hybrid = store_bytes(e, STORE_HYBRID);
     const bool fits_group = b_group > 0 && b_group <= per_block_max;
-    const bool fits_hybrid = b_hybrid > 0 && b_hybrid <= per_block_max;
+    const bool fits_hybrid = b_hybrid > 0 && b_hybrid <= per_block_max && e->S <= 64;   // DevParams::row_lut holds 64 states
     int want = e->cfg.store_kind;
     if (e->cfg.planning_steps) {
         // planning replays arbitrary remembered states, terminal ones included, and the model itself lives in HBM
@@ -303,7 +321,7 @@ rlb_status install_selector(rlb_engine* e, int kind) {
 
 size_t episode_rec_size(const rlb_engine* e) { return e->cfg.real_kind == RLB_REAL_F32 ? sizeof(rlb_episode_f32) : sizeof(rlb_episode_f64); }
 
-rlb_status ensure_episode_scratch(rlb_engine* e, uint64_t episodes) {
+rlb_status ensure_episode_scratch(rlb_engine* e, uint64_t episodes, uint64_t sums_episodes) {
     const size_t need = (size_t)episodes * e->cfg.n_agents * episode_rec_size(e);
     if (e->episodes_cap < need) {
         if (e->d_episodes) cudaFree(e->d_episodes);
@@ -311,7 +329,7 @@ rlb_status ensure_episode_scratch(rlb_engine* e, uint64_t episodes) {
         CK(cudaMalloc(&e->d_episodes, need));
         e->episodes_cap = need;
     }
-    const size_t need_s = (size_t)episodes * 4 * sizeof(double);
+    const size_t need_s = (size_t)sums_episodes * 4 * sizeof(double);
     if (e->sums_cap < need_s) {
         if (e->d_sums) cudaFree(e->d_sums);
         e->d_sums = nullptr; e->sums_cap = 0;
@@ -331,11 +349,10 @@ uint64_t chunk_episodes(const rlb_engine* e, uint64_t want) {
     return std::min<uint64_t>(chunk, std::max<uint64_t>(want, 1));
 }
 
-rlb_status reduce_episodes(rlb_engine* e, uint64_t n_ep, const void* records = nullptr) {
+rlb_status reduce_episodes(rlb_engine* e, uint64_t n_ep, const void* records, double* sums_out) {
     if (!n_ep) return RLB_OK;
-    if (!records) records = e->d_episodes;
-    if (e->cfg.real_kind == RLB_REAL_F32) k_episode_sums<float><<<(unsigned)n_ep, 256, 0, e->stream>>>(records, e->cfg.n_agents, e->d_sums);
-    else k_episode_sums<double><<<(unsigned)n_ep, 256, 0, e->stream>>>(records, e->cfg.n_agents, e->d_sums);
+    if (e->cfg.real_kind == RLB_REAL_F32) k_episode_sums<float><<<(unsigned)n_ep, 256, 0, e->stream>>>(records, e->cfg.n_agents, sums_out);
+    else k_episode_sums<double><<<(unsigned)n_ep, 256, 0, e->stream>>>(records, e->cfg.n_agents, sums_out);
     CK(cudaGetLastError());
     return RLB_OK;
 }
@@ -362,12 +379,198 @@ bool valid_cfg(const rlb_config* c) {
     return true;
 }
 
+// The flag word the step-level kernels raise (FLAG_* in rlb_step_kernels.cuh): cleared before the launch, read after it.
+cudaError_t flags_clear(rlb_engine* e) { return cudaMemsetAsync(e->d_flagword, 0, 4, e->stream); }
+rlb_status flags_check(rlb_engine* e) {
+    uint32_t any = 0;
+    CK(cudaMemcpyAsync(&any, e->d_flagword, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (any & FLAG_BAD_ARG) {
+        set_error("observation, action or model entry out of range for this env (the reference would panic on the same index); the agents concerned were left untouched");
+        return RLB_ERR_INVALID_ARG;
+    }
+    if (any & FLAG_TRACE_FULL) {
+        set_error("update(): the eligibility trace would exceed the %u rows the engine holds per agent (episodes of its own env never do)", e->dp.vmax);
+        return RLB_ERR_INVALID_ARG;
+    }
+    if (any & FLAG_DEAD_STATE) {
+        set_error("update(): curr_obs is a terminal cell of the env (never an observation an action is taken from); unsupported by the trace agent's table stores");
+        return RLB_ERR_UNSUPPORTED;
+    }
+    if (any & FLAG_NOT_READY) { set_error("EnvNotReady: step() before reset() or after termination"); return RLB_ERR_ENV_NOT_READY; }
+    return RLB_OK;
+}
+
+// ---- the fused path: enqueue everything, wait later -------------------------------------------------------------
+cudaEvent_t take_event(rlb_engine* e) {
+    if (!e->event_pool.empty()) { cudaEvent_t ev = e->event_pool.back(); e->event_pool.pop_back(); return ev; }
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreate(&ev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return ev;
+}
+
+// Block until the OLDEST pending call is complete and fill its outputs.
+rlb_status finish_oldest(rlb_engine* e) {
+    if (e->pending.empty()) return RLB_OK;
+    rlb_engine::Pending pd = std::move(e->pending.front());
+    e->pending.erase(e->pending.begin());
+    rlb_status status = RLB_OK;
+    auto note = [&](cudaError_t err, const char* what) { if (err != cudaSuccess && status == RLB_OK) status = cuda_fail(err, what); };
+    note(cudaEventSynchronize(pd.done), "cudaEventSynchronize(done)");                  // kernels, reductions, sums and totals copies
+    if (pd.copies_done) note(cudaEventSynchronize(pd.copies_done), "cudaEventSynchronize(copies)");   // this call's records are in host memory
+    float ms_total = 0.f;
+    for (size_t k = 0; k + 1 < pd.events.size(); k += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pd.events[k], pd.events[k + 1]) == cudaSuccess) ms_total += ms; else cudaGetLastError();
+    }
+    const uint32_t launches = (uint32_t)(pd.events.size() / 2);
+    for (cudaEvent_t ev : pd.events) e->event_pool.push_back(ev);
+    e->event_pool.push_back(pd.done);
+    if (pd.copies_done) e->event_pool.push_back(pd.copies_done);
+    unsigned long long totals[8];
+    std::memcpy(totals, pd.h_totals, sizeof totals);
+    e->totals_pool.push_back(pd.h_totals);
+    const uint64_t N = e->cfg.n_agents;
+    if (pd.d_traj) {
+        if (pd.own_traj) { note(copy_out(e, pd.out->traj, pd.d_traj, N * pd.out->traj_capacity * sizeof(rlb_traj_record)), "copy traj"); cudaFree(pd.d_traj); }
+        if (pd.own_count) { if (pd.out->traj_count) note(copy_out(e, pd.out->traj_count, pd.d_traj_count, N * sizeof(uint64_t)), "copy traj_count"); cudaFree(pd.d_traj_count); }
+    }
+    if (pd.d_td) {
+        if (pd.own_td) { note(copy_out(e, pd.out->td_steps, pd.d_td, N * pd.out->td_capacity * e->real_size), "copy td_steps"); cudaFree(pd.d_td); }
+        if (pd.own_td_count) { if (pd.out->td_count) note(copy_out(e, pd.out->td_count, pd.d_td_count, N * sizeof(uint64_t)), "copy td_count"); cudaFree(pd.d_td_count); }
+    }
+    if (pd.mode == 0 && pd.out) {
+        pd.out->train_steps = totals[0]; pd.out->eval_steps = totals[1]; pd.out->eval_episodes = totals[2];
+        pd.out->eval_return_sum = (double)(long long)totals[3];   // an exact integer (rlb_device.cuh, LaneTotals)
+        pd.out->kernel_ms = ms_total; pd.out->kernel_launches = launches; pd.out->trace_rows = totals[4];
+    }
+    if (pd.mode == 1 && pd.eval_steps_out) *pd.eval_steps_out = totals[1];
+    return status;
+}
+rlb_status finish_pending(rlb_engine* e) {
+    rlb_status status = RLB_OK;
+    while (!e->pending.empty()) {
+        rlb_status st = finish_oldest(e);
+        if (status == RLB_OK) status = st;
+    }
+    return status;
+}
+// every entry point but the asynchronous train call: select the device, complete what is pending
+#define ENTER(e)                                           \
+    do {                                                   \
+        CK(cudaSetDevice((e)->cfg.device));                \
+        rlb_status st__ = finish_pending(e);               \
+        if (st__ != RLB_OK) return st__;                   \
+    } while (0)
+
+rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, uint64_t eval_at, rlb_train_out* out,
+                         void* eval_episodes_out, double* eval_sums_out, uint64_t* eval_steps_out) {
+    const uint64_t N = e->cfg.n_agents;
+    const size_t rec = episode_rec_size(e);
+    const uint64_t total = end - begin;
+    const bool want_records = mode == 0 ? (out && (out->episodes || out->episode_sums)) : (eval_episodes_out || eval_sums_out);
+    uint64_t chunk = std::min<uint64_t>(total, 0xffffffffull);   // a launch counts its episodes in 32 bits
+    // Records for a HOST buffer are pipelined: the range is cut into (at least) four launches writing alternately into
+    // the two halves of the scratch, and while launch i + 1 runs the records of launch i travel to the host on a second
+    // stream — the PCIe copy (1.7 GB per step on C2, 3.2 GB on C4) hides behind the kernels, the tail of the last copy
+    // behind the NEXT call's kernels when the caller uses the asynchronous form.
+    void* const rec_host = mode == 0 ? (out ? out->episodes : nullptr) : eval_episodes_out;
+    const bool pipelined = rec_host && !is_device_ptr(rec_host) && total >= 8;
+    if (want_records) {
+        chunk = std::min<uint64_t>(chunk, chunk_episodes(e, total));
+        if (pipelined) chunk = std::max<uint64_t>(1, std::min<uint64_t>((chunk + 1) / 2, (total + 3) / 4));
+    }
+    // A call may only overlap the one before it when both stream records through the same two scratch halves.
+    if (!e->pending.empty() && !(pipelined && e->pending.back().pipelined && chunk == e->last_pipeline_chunk && total <= e->sums_cap / (4 * sizeof(double)))) {
+        rlb_status st = finish_pending(e);
+        if (st != RLB_OK) return st;
+    }
+    if (want_records) {
+        rlb_status st = ensure_episode_scratch(e, pipelined ? 2 * chunk : chunk, total);
+        if (st != RLB_OK) return st;
+        if (pipelined) { st = ensure_copy_pipeline(e); if (st != RLB_OK) return st; e->last_pipeline_chunk = chunk; }
+    }
+    rlb_engine::Pending pd;
+    pd.mode = mode; pd.out = out; pd.eval_steps_out = eval_steps_out; pd.pipelined = pipelined;
+    if (e->totals_pool.empty()) {
+        unsigned long long* h = nullptr;
+        CK(cudaHostAlloc(&h, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+        e->totals_pool.push_back(h);
+    }
+    pd.h_totals = e->totals_pool.back(); e->totals_pool.pop_back();
+    // trajectory tap and per-step TD stream: device scratch when the caller's buffers are on the host
+    if (mode == 0 && out && out->traj && out->traj_capacity) {
+        if (is_device_ptr(out->traj)) pd.d_traj = out->traj;
+        else { CK(cudaMalloc(&pd.d_traj, N * out->traj_capacity * sizeof(rlb_traj_record))); pd.own_traj = true; }
+        if (out->traj_count && is_device_ptr(out->traj_count)) pd.d_traj_count = out->traj_count;
+        else { CK(cudaMalloc(&pd.d_traj_count, N * sizeof(uint64_t))); pd.own_count = true; }
+        CK(cudaMemsetAsync(pd.d_traj_count, 0, N * sizeof(uint64_t), e->stream));
+    }
+    if (mode == 0 && out && out->td_steps && out->td_capacity) {
+        if (is_device_ptr(out->td_steps)) pd.d_td = out->td_steps;
+        else { CK(cudaMalloc(&pd.d_td, N * out->td_capacity * e->real_size)); pd.own_td = true; }
+        if (out->td_count && is_device_ptr(out->td_count)) pd.d_td_count = out->td_count;
+        else { CK(cudaMalloc(&pd.d_td_count, N * sizeof(uint64_t))); pd.own_td_count = true; }
+        CK(cudaMemsetAsync(pd.d_td_count, 0, N * sizeof(uint64_t), e->stream));
+    }
+    CK(cudaMemsetAsync(e->d_totals, 0, 8 * sizeof(unsigned long long), e->stream));
+    double* const sums_dst = mode == 0 ? (out ? out->episode_sums : nullptr) : eval_sums_out;
+    void* const rec_dst = mode == 0 ? (out ? out->episodes : nullptr) : eval_episodes_out;
+    for (uint64_t c0 = begin; c0 < end; c0 += chunk) {
+        const uint64_t c1 = std::min<uint64_t>(end, c0 + chunk);
+        const int half = pipelined ? (int)(e->launch_counter & 1) : 0;
+        if (pipelined) e->launch_counter += 1;
+        char* const scratch = (char*)e->d_episodes + (pipelined ? (size_t)half * chunk * N * rec : 0);
+        // this half's previous records — of this call or of the one before it — must have left
+        if (pipelined) CK(cudaStreamWaitEvent(e->stream, e->ev_drained[half], 0));
+        DevParams p = e->dp;
+        p.mode = mode;
+        p.eval_at = eval_at;
+        if (mode == 0) { p.ep0 = c0; p.ep1 = c1; p.n_eval = 0; }
+        else { p.ep0 = p.ep1 = 0; p.n_eval = c1 - c0; }
+        p.episodes = want_records ? scratch : nullptr;
+        p.traj = pd.d_traj; p.traj_cap = pd.d_traj ? out->traj_capacity : 0; p.traj_count = pd.d_traj_count;
+        p.td_steps = pd.d_td; p.td_cap = pd.d_td ? out->td_capacity : 0; p.td_count = pd.d_td_count;
+        cudaEvent_t ev0 = take_event(e), ev1 = take_event(e);
+        if (!ev0 || !ev1) { set_error("cudaEventCreate failed"); return RLB_ERR_CUDA; }
+        pd.events.push_back(ev0); pd.events.push_back(ev1);
+        CK(cudaEventRecord(ev0, e->stream));
+        CK(dispatch_run(e, p));
+        CK(cudaEventRecord(ev1, e->stream));
+        const uint64_t n_ep = c1 - c0;
+        if (sums_dst) {   // reads the records on the main stream, before that scratch is written again
+            rlb_status st = reduce_episodes(e, n_ep, scratch, e->d_sums + (c0 - begin) * 4);
+            if (st != RLB_OK) return st;
+        }
+        if (pipelined) {
+            CK(cudaEventRecord(e->ev_filled[half], e->stream));
+            CK(cudaStreamWaitEvent(e->copy_stream, e->ev_filled[half], 0));
+            CK(cudaMemcpyAsync((char*)rec_dst + (c0 - begin) * N * rec, scratch, n_ep * N * rec, cudaMemcpyDeviceToHost, e->copy_stream));
+            CK(cudaEventRecord(e->ev_drained[half], e->copy_stream));
+        } else if (rec_dst) {
+            CK(copy_async(e, (char*)rec_dst + (c0 - begin) * N * rec, scratch, n_ep * N * rec));
+        }
+    }
+    if (sums_dst && total) CK(copy_async(e, sums_dst, e->d_sums, total * 4 * sizeof(double)));
+    CK(cudaMemcpyAsync(pd.h_totals, e->d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    pd.done = take_event(e);
+    if (!pd.done) { set_error("cudaEventCreate failed"); return RLB_ERR_CUDA; }
+    CK(cudaEventRecord(pd.done, e->stream));
+    if (pipelined) {
+        pd.copies_done = take_event(e);
+        if (!pd.copies_done) { set_error("cudaEventCreate failed"); return RLB_ERR_CUDA; }
+        CK(cudaEventRecord(pd.copies_done, e->copy_stream));
+    }
+    e->pending.push_back(std::move(pd));
+    return RLB_OK;
+}
+
 }   // namespace
 
 extern "C" {
 
 int rlb_abi_version(void) { return RLB_ABI_VERSION; }
-const char* rlb_last_error_string(void) { return g_last_error.c_str(); }
+const char* rlb_last_error_string(void) { return last_error_cstr(); }
 int rlb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -452,7 +655,10 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     }
     p.mode = 0; p.eval_episodes = 100; p.ep0 = p.ep1 = 0; p.eval_at = 1; p.n_eval = 0;
     p.episodes = nullptr; p.traj = nullptr; p.traj_cap = 0; p.traj_count = nullptr;
-    p.totals = e->d_totals; p.eval_ret_total = reinterpret_cast<double*>(e->d_totals + 3);
+    p.totals = e->d_totals;
+    p.td_steps = nullptr; p.td_cap = 0; p.td_count = nullptr;
+    p.cur_obs = nullptr; p.cur_action = nullptr;
+    p.fl_start = e->tables.fl_start;
     p.model_ent = nullptr; p.model_bits = nullptr; p.model_len = nullptr; p.planning_steps = 0; p.mcap = 0; p.mwords = 0;
 
     CKE(fill_q_default(e));
@@ -475,7 +681,13 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
 void rlb_engine_destroy(rlb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    finish_pending(e);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+    for (unsigned long long* h : e->totals_pool) cudaFreeHost(h);
+    if (e->d_cur_obs) cudaFree(e->d_cur_obs);
+    if (e->d_cur_action) cudaFree(e->d_cur_action);
+    if (e->d_log_table) cudaFree(e->d_log_table);
     void* bufs[] = {e->d_q, e->d_counts, e->d_etr, e->d_etr_il, e->d_vis, e->d_nvis, e->d_rng_n, e->d_eps, e->d_ucb_t, e->d_flag, e->d_env,
                     e->d_trans, e->d_thr, e->d_thr_state, e->d_totals, e->d_flagword, e->d_episodes, e->d_sums,
                     e->d_model_ent, e->d_model_bits, e->d_model_len};
@@ -495,7 +707,7 @@ void rlb_engine_destroy(rlb_engine* e) {
 
 rlb_status rlb_engine_set_stream(rlb_engine* e, void* cuda_stream) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     CK(cudaStreamSynchronize(e->stream));
     if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
     e->stream = (cudaStream_t)cuda_stream;
@@ -503,7 +715,7 @@ rlb_status rlb_engine_set_stream(rlb_engine* e, void* cuda_stream) {
 }
 rlb_status rlb_engine_synchronize(rlb_engine* e) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     CK(cudaStreamSynchronize(e->stream));
     return RLB_OK;
 }
@@ -519,7 +731,7 @@ uint32_t rlb_engine_store_kind(const rlb_engine* e) { return e ? (uint32_t)e->st
 // ------------------------------------------------------------------------------- Env
 rlb_status rlb_env_reset(rlb_engine* e, uint32_t* obs_out) {
     if (!e || !obs_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     StepArgs a;
     void* dev;
@@ -533,7 +745,7 @@ rlb_status rlb_env_reset(rlb_engine* e, uint32_t* obs_out) {
 rlb_status rlb_env_step(rlb_engine* e, const uint32_t* actions, uint32_t* obs_out, double* reward_out, uint8_t* terminated_out,
                         uint8_t* not_ready_out) {
     if (!e || !actions || !obs_out || !reward_out || !terminated_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     StepArgs a;
     const void* in;
@@ -546,39 +758,36 @@ rlb_status rlb_env_step(rlb_engine* e, const uint32_t* actions, uint32_t* obs_ou
     CK(stage_out(e, 4, not_ready_out, N, &d_nr));
     a.u32_out = (uint32_t*)d_obs; a.reward_out = (double*)d_rew; a.term_out = (uint8_t*)d_term; a.not_ready_out = (uint8_t*)d_nr;
     a.any_not_ready = e->d_flagword;
-    CK(cudaMemsetAsync(e->d_flagword, 0, 4, e->stream));
+    CK(flags_clear(e));
     CK(dispatch_step(e, OP_ENV_STEP, a));
-    uint32_t any = 0;
-    CK(cudaMemcpyAsync(&any, e->d_flagword, 4, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
     CK(finish_out(e, obs_out, d_obs, N * 4));
     CK(finish_out(e, reward_out, d_rew, N * 8));
     CK(finish_out(e, terminated_out, d_term, N));
     CK(finish_out(e, not_ready_out, d_nr, N));
-    if (any) { set_error("EnvNotReady: step() before reset() or after termination"); return RLB_ERR_ENV_NOT_READY; }
-    return RLB_OK;
+    return flags_check(e);
 }
 
 // ------------------------------------------------------------------------------- Agent
 rlb_status rlb_agent_get_action(rlb_engine* e, const uint32_t* obs, uint32_t* action_out) {
     if (!e || !obs || !action_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     StepArgs a;
     const void* in;
     void* dev;
     CK(stage_in(e, 0, obs, N * 4, &in));
     CK(stage_out(e, 1, action_out, N * 4, &dev));
-    a.obs = (const uint32_t*)in; a.u32_out = (uint32_t*)dev;
+    a.obs = (const uint32_t*)in; a.u32_out = (uint32_t*)dev; a.any_not_ready = e->d_flagword;
+    CK(flags_clear(e));
     CK(dispatch_step(e, OP_GET_ACTION, a));
     CK(finish_out(e, action_out, dev, N * 4));
-    return RLB_OK;
+    return flags_check(e);
 }
 
 rlb_status rlb_agent_update(rlb_engine* e, const uint32_t* curr_obs, const uint32_t* curr_action, const double* reward,
                             const uint8_t* terminated, const uint32_t* next_obs, const uint32_t* next_action, void* td_out) {
     if (!e || !curr_obs || !curr_action || !reward || !terminated || !next_obs || !next_action) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     StepArgs a;
     const void* in[6];
@@ -592,9 +801,43 @@ rlb_status rlb_agent_update(rlb_engine* e, const uint32_t* curr_obs, const uint3
     CK(stage_out(e, 6, td_out, N * e->real_size, &dev));
     a.obs = (const uint32_t*)in[0]; a.action = (const uint32_t*)in[1]; a.reward = (const double*)in[2];
     a.term = (const uint8_t*)in[3]; a.obs2 = (const uint32_t*)in[4]; a.action2 = (const uint32_t*)in[5];
-    a.real_out = dev;
+    a.real_out = dev; a.any_not_ready = e->d_flagword;
+    CK(flags_clear(e));
     CK(dispatch_step(e, OP_UPDATE, a));
     CK(finish_out(e, td_out, dev, N * e->real_size));
+    return flags_check(e);
+}
+
+rlb_status rlb_agent_step(rlb_engine* e, uint8_t* kind_out, uint32_t* obs_out, uint32_t* action_out, double* reward_out,
+                          uint8_t* terminated_out, void* td_out) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    ENTER(e);
+    const uint64_t N = e->cfg.n_agents;
+    if (!e->d_cur_obs) {
+        CK(cudaMalloc(&e->d_cur_obs, N * 4));
+        CK(cudaMalloc(&e->d_cur_action, N * 4));
+        CK(cudaMemsetAsync(e->d_cur_obs, 0, N * 4, e->stream));
+        CK(cudaMemsetAsync(e->d_cur_action, 0, N * 4, e->stream));
+        e->dp.cur_obs = e->d_cur_obs; e->dp.cur_action = e->d_cur_action;
+    }
+    StepArgs a;
+    void *d_kind, *d_obs, *d_act, *d_rew, *d_term, *d_td;
+    CK(stage_out(e, 0, kind_out, N, &d_kind));
+    CK(stage_out(e, 1, obs_out, N * 4, &d_obs));
+    CK(stage_out(e, 2, action_out, N * 4, &d_act));
+    CK(stage_out(e, 3, reward_out, N * 8, &d_rew));
+    CK(stage_out(e, 4, terminated_out, N, &d_term));
+    CK(stage_out(e, 5, td_out, N * e->real_size, &d_td));
+    a.kind_out = (uint8_t*)d_kind; a.u32_out = (uint32_t*)d_obs; a.u32_out2 = (uint32_t*)d_act; a.reward_out = (double*)d_rew;
+    a.term_out = (uint8_t*)d_term; a.real_out = d_td;
+    CK(dispatch_step(e, OP_AGENT_STEP, a));
+    // one wait for the whole call: the copies of the (small) outputs ride the stream
+    CK(copy_async(e, kind_out, d_kind, kind_out == d_kind ? 0 : N));
+    CK(copy_async(e, obs_out, d_obs, obs_out == d_obs ? 0 : N * 4));
+    CK(copy_async(e, action_out, d_act, action_out == d_act ? 0 : N * 4));
+    CK(copy_async(e, reward_out, d_rew, reward_out == d_rew ? 0 : N * 8));
+    CK(copy_async(e, terminated_out, d_term, terminated_out == d_term ? 0 : N));
+    CK(copy_async(e, td_out, d_td, td_out == d_td ? 0 : N * e->real_size));
     CK(cudaStreamSynchronize(e->stream));
     return RLB_OK;
 }
@@ -608,7 +851,7 @@ rlb_status rlb_agent_set_future_q_value_func(rlb_engine* e, int32_t target_kind)
 
 rlb_status rlb_agent_set_action_selector(rlb_engine* e, int32_t selector_kind) {
     if (!e || selector_kind < 0 || selector_kind > 1) { set_error("bad selector_kind"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     rlb_status st = install_selector(e, selector_kind);
     if (st != RLB_OK) return st;
     return pick_store(e);
@@ -616,7 +859,7 @@ rlb_status rlb_agent_set_action_selector(rlb_engine* e, int32_t selector_kind) {
 
 rlb_status rlb_agent_set_kind(rlb_engine* e, int32_t agent_kind) {
     if (!e || agent_kind < 0 || agent_kind > 1) { set_error("bad agent_kind"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     e->cfg.agent_kind = agent_kind;
     e->variant.trace = agent_kind == RLB_AGENT_TRACES ? 1 : 0;
@@ -638,7 +881,7 @@ rlb_status rlb_agent_set_kind(rlb_engine* e, int32_t agent_kind) {
 
 rlb_status rlb_selector_reset(rlb_engine* e) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     if (e->cfg.selector_kind == RLB_SEL_EPS_GREEDY) {
         CK(fill<double>(e, e->d_eps, N, e->cfg.initial_epsilon));               // uniform_epsilon_greed.rs:78-80
@@ -651,7 +894,7 @@ rlb_status rlb_selector_reset(rlb_engine* e) {
 
 rlb_status rlb_policy_reset(rlb_engine* e) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     CK(fill_q_default(e));   // tables back to the default row; Double keeps its flag (double_tabular_policy.rs:60-63)
     return RLB_OK;
 }
@@ -666,7 +909,7 @@ rlb_status rlb_agent_reset(rlb_engine* e) {   // one_step_agent.rs:43-46: action
 
 rlb_status rlb_agent_set_model(rlb_engine* e, uint32_t planning_steps) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     if (planning_steps && e->cfg.store_kind != 0 && e->cfg.store_kind != STORE_GLOBAL) {
         set_error("a Dyna model (planning_steps > 0) needs the HBM store");
         return RLB_ERR_UNSUPPORTED;
@@ -680,23 +923,23 @@ rlb_status rlb_agent_set_model(rlb_engine* e, uint32_t planning_steps) {
 rlb_status rlb_model_add_info(rlb_engine* e, const uint32_t* obs, const uint32_t* action, const double* reward, const uint32_t* next_obs) {
     if (!e || !obs || !action || !reward || !next_obs) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
     if (!e->cfg.planning_steps) { set_error("no model attached (rlb_agent_set_model)"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     const void* in[4];
     CK(stage_in(e, 0, obs, N * 4, &in[0]));
     CK(stage_in(e, 1, action, N * 4, &in[1]));
     CK(stage_in(e, 2, reward, N * 8, &in[2]));
     CK(stage_in(e, 3, next_obs, N * 4, &in[3]));
+    CK(flags_clear(e));
     k_model_add_info<<<(unsigned)((N + 127) / 128), 128, 0, e->stream>>>(e->dp, e->A, (const uint32_t*)in[0], (const uint32_t*)in[1],
-                                                                         (const double*)in[2], (const uint32_t*)in[3]);
+                                                                         (const double*)in[2], (const uint32_t*)in[3], e->d_flagword);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(e->stream));
-    return RLB_OK;
+    return flags_check(e);
 }
 rlb_status rlb_model_get_info(rlb_engine* e, uint32_t* obs_out, uint32_t* action_out, uint32_t* next_obs_out, double* reward_out) {
     if (!e || !obs_out || !action_out || !next_obs_out || !reward_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
     if (!e->cfg.planning_steps) { set_error("no model attached (rlb_agent_set_model)"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     void* dev[4];
     CK(stage_out(e, 0, obs_out, N * 4, &dev[0]));
@@ -720,7 +963,7 @@ rlb_status rlb_model_get_info(rlb_engine* e, uint32_t* obs_out, uint32_t* action
 rlb_status rlb_model_reset(rlb_engine* e) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
     if (!e->cfg.planning_steps) return RLB_OK;
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     CK(cudaMemsetAsync(e->d_model_bits, 0, (size_t)N * e->dp.mwords * sizeof(uint32_t), e->stream));
     CK(cudaMemsetAsync(e->d_model_len, 0, N * sizeof(uint32_t), e->stream));
@@ -730,7 +973,7 @@ uint32_t rlb_model_capacity(const rlb_engine* e) { return e ? e->dp.mcap : 0u; }
 rlb_status rlb_download_model(rlb_engine* e, uint32_t* len_out, rlb_model_entry* entries_out) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
     if (!e->cfg.planning_steps) { set_error("no model attached (rlb_agent_set_model)"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     if (len_out) CK(copy_out(e, len_out, e->d_model_len, N * 4));
     if (entries_out) {
@@ -747,140 +990,75 @@ rlb_status rlb_download_model(rlb_engine* e, uint32_t* len_out, rlb_model_entry*
 rlb_status rlb_upload_model(rlb_engine* e, const uint32_t* len, const rlb_model_entry* entries) {
     if (!e || !len || !entries) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
     if (!e->cfg.planning_steps) { set_error("no model attached (rlb_agent_set_model)"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     const void* in[2];
     CK(stage_in(e, 0, len, N * 4, &in[0]));
     CK(stage_in(e, 7, entries, (size_t)N * e->dp.mcap * sizeof(rlb_model_entry), &in[1]));
-    k_model_import<<<(unsigned)((N + 127) / 128), 128, 0, e->stream>>>(e->dp, e->A, (const uint32_t*)in[0], (const rlb_model_entry*)in[1]);
+    CK(flags_clear(e));
+    k_model_import<<<(unsigned)((N + 127) / 128), 128, 0, e->stream>>>(e->dp, e->A, (const uint32_t*)in[0], (const rlb_model_entry*)in[1], e->d_flagword);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(e->stream));
-    return RLB_OK;
+    return flags_check(e);
 }
 
-static rlb_status run_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, uint64_t eval_at, rlb_train_out* out,
-                            void* eval_episodes_out, double* eval_sums_out, uint64_t* eval_steps_out) {
-    CK(cudaSetDevice(e->cfg.device));
-    const uint64_t N = e->cfg.n_agents;
-    const size_t rec = episode_rec_size(e);
-    const uint64_t total = end - begin;
-    const bool want_records = mode == 0 ? (out && (out->episodes || out->episode_sums)) : (eval_episodes_out || eval_sums_out);
-    uint64_t chunk = total;
-    // Records for a HOST buffer are pipelined: the range is cut into (at least) four launches writing alternately into
-    // the two halves of the scratch, and while launch i + 1 runs the records of launch i travel to the host on a second
-    // stream — the PCIe copy (1.7 GB per step on C2, 3.2 GB on C4) hides behind the kernels except for its last part.
-    void* const rec_host = mode == 0 ? (out ? out->episodes : nullptr) : eval_episodes_out;
-    const bool pipelined = rec_host && !is_device_ptr(rec_host) && total >= 8;
-    if (want_records) {
-        chunk = chunk_episodes(e, total);
-        if (pipelined) chunk = std::max<uint64_t>(1, std::min<uint64_t>((chunk + 1) / 2, (total + 3) / 4));
-        rlb_status st = ensure_episode_scratch(e, pipelined ? 2 * chunk : chunk);
-        if (st != RLB_OK) return st;
-        if (pipelined) { st = ensure_copy_pipeline(e); if (st != RLB_OK) return st; }
-    }
-    // trajectory tap
-    rlb_traj_record* d_traj = nullptr;
-    uint64_t* d_traj_count = nullptr;
-    bool own_traj = false, own_count = false;
-    if (mode == 0 && out && out->traj && out->traj_capacity) {
-        if (is_device_ptr(out->traj)) d_traj = out->traj;
-        else { CK(cudaMalloc(&d_traj, N * out->traj_capacity * sizeof(rlb_traj_record))); own_traj = true; }
-        if (out->traj_count && is_device_ptr(out->traj_count)) d_traj_count = out->traj_count;
-        else { CK(cudaMalloc(&d_traj_count, N * sizeof(uint64_t))); own_count = true; }
-        CK(cudaMemsetAsync(d_traj_count, 0, N * sizeof(uint64_t), e->stream));
-    }
-    CK(cudaMemsetAsync(e->d_totals, 0, 8 * sizeof(unsigned long long), e->stream));
-    float ms_total = 0.f;
-    uint32_t launches = 0;
-    uint64_t launch_index = 0;
-    for (uint64_t c0 = begin; c0 < end; c0 += chunk, ++launch_index) {
-        const uint64_t c1 = std::min<uint64_t>(end, c0 + chunk);
-        const int half = pipelined ? (int)(launch_index & 1) : 0;
-        char* const scratch = (char*)e->d_episodes + (pipelined ? (size_t)half * chunk * N * rec : 0);
-        if (pipelined && launch_index >= 2) CK(cudaStreamWaitEvent(e->stream, e->ev_drained[half], 0));   // this half's previous records have left
-        DevParams p = e->dp;
-        p.mode = mode;
-        p.eval_at = eval_at;
-        if (mode == 0) { p.ep0 = c0; p.ep1 = c1; p.n_eval = 0; }
-        else { p.ep0 = p.ep1 = 0; p.n_eval = c1 - c0; }
-        p.episodes = want_records ? scratch : nullptr;
-        p.traj = d_traj; p.traj_cap = d_traj ? out->traj_capacity : 0; p.traj_count = d_traj_count;
-        CK(cudaEventRecord(e->ev0, e->stream));
-        CK(dispatch_run(e, p));
-        CK(cudaEventRecord(e->ev1, e->stream));
-        launches += 1;
-        const uint64_t n_ep = c1 - c0;
-        double* sums_dst = mode == 0 ? (out ? out->episode_sums : nullptr) : eval_sums_out;
-        void* rec_dst = mode == 0 ? (out ? out->episodes : nullptr) : eval_episodes_out;
-        if (pipelined) {
-            CK(cudaEventRecord(e->ev_filled[half], e->stream));
-            CK(cudaStreamWaitEvent(e->copy_stream, e->ev_filled[half], 0));
-            CK(cudaMemcpyAsync((char*)rec_dst + (c0 - begin) * N * rec, scratch, n_ep * N * rec, cudaMemcpyDeviceToHost, e->copy_stream));
-            CK(cudaEventRecord(e->ev_drained[half], e->copy_stream));
-            if (sums_dst) {   // the reduction reads the same half: it runs on the main stream, before the half is written again
-                rlb_status st = reduce_episodes(e, n_ep, scratch);
-                if (st != RLB_OK) return st;
-                CK(copy_out(e, sums_dst + (c0 - begin) * 4, e->d_sums, n_ep * 4 * sizeof(double)));
-            }
-        } else {
-            if (sums_dst) {
-                rlb_status st = reduce_episodes(e, n_ep);
-                if (st != RLB_OK) return st;
-                CK(copy_out(e, sums_dst + (c0 - begin) * 4, e->d_sums, n_ep * 4 * sizeof(double)));
-            }
-            if (rec_dst) CK(copy_out(e, (char*)rec_dst + (c0 - begin) * N * rec, e->d_episodes, n_ep * N * rec));
-        }
-        CK(cudaEventSynchronize(e->ev1));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
-        ms_total += ms;
-    }
-    if (pipelined) CK(cudaStreamSynchronize(e->copy_stream));
-    unsigned long long totals[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CK(cudaMemcpyAsync(totals, e->d_totals, sizeof totals, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    if (d_traj) {
-        if (own_traj) { CK(copy_out(e, out->traj, d_traj, N * out->traj_capacity * sizeof(rlb_traj_record))); cudaFree(d_traj); }
-        if (own_count) { if (out->traj_count) CK(copy_out(e, out->traj_count, d_traj_count, N * sizeof(uint64_t))); cudaFree(d_traj_count); }
-    }
-    double eval_ret;
-    std::memcpy(&eval_ret, &totals[3], 8);
-    if (mode == 0 && out) {
-        out->train_steps = totals[0]; out->eval_steps = totals[1]; out->eval_episodes = totals[2];
-        out->eval_return_sum = eval_ret; out->kernel_ms = ms_total; out->kernel_launches = launches; out->trace_rows = totals[4];
-    }
-    if (mode == 1 && eval_steps_out) *eval_steps_out = totals[1];
-    return RLB_OK;
-}
-
-rlb_status rlb_agent_train_range(rlb_engine* e, uint64_t ep_begin, uint64_t ep_end, uint64_t eval_at, rlb_train_out* out) {
+static rlb_status check_train_args(rlb_engine* e, uint64_t ep_begin, uint64_t ep_end, uint64_t eval_at) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
     if (eval_at == 0) { set_error("eval_at == 0 (the reference divides by it, agent.rs:107)"); return RLB_ERR_INVALID_ARG; }
     if (ep_end < ep_begin) { set_error("ep_end < ep_begin"); return RLB_ERR_INVALID_ARG; }
-    return run_range(e, 0, ep_begin, ep_end, eval_at, out, nullptr, nullptr, nullptr);
+    return RLB_OK;
+}
+rlb_status rlb_agent_train_range(rlb_engine* e, uint64_t ep_begin, uint64_t ep_end, uint64_t eval_at, rlb_train_out* out) {
+    rlb_status st = check_train_args(e, ep_begin, ep_end, eval_at);
+    if (st != RLB_OK) return st;
+    ENTER(e);
+    st = enqueue_range(e, 0, ep_begin, ep_end, eval_at, out, nullptr, nullptr, nullptr);
+    rlb_status st2 = finish_pending(e);
+    return st != RLB_OK ? st : st2;
+}
+rlb_status rlb_agent_train_range_async(rlb_engine* e, uint64_t ep_begin, uint64_t ep_end, uint64_t eval_at, rlb_train_out* out) {
+    rlb_status st = check_train_args(e, ep_begin, ep_end, eval_at);
+    if (st != RLB_OK) return st;
+    CK(cudaSetDevice(e->cfg.device));
+    st = enqueue_range(e, 0, ep_begin, ep_end, eval_at, out, nullptr, nullptr, nullptr);
+    if (st != RLB_OK) { finish_pending(e); return st; }
+    // the new call's kernels are in the queue: now the host may block on the call before it
+    while (e->pending.size() > 1) {
+        st = finish_oldest(e);
+        if (st != RLB_OK) return st;
+    }
+    return RLB_OK;
+}
+rlb_status rlb_agent_train_wait(rlb_engine* e) {
+    if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(e->cfg.device));
+    return finish_pending(e);
 }
 rlb_status rlb_agent_train(rlb_engine* e, uint64_t n_episodes, uint64_t eval_at, rlb_train_out* out) {
     return rlb_agent_train_range(e, 0, n_episodes, eval_at, out);
 }
 rlb_status rlb_agent_evaluate(rlb_engine* e, uint64_t n_episodes, void* episodes_out, double* sums_out, uint64_t* total_steps_out) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    return run_range(e, 1, 0, n_episodes, 1, nullptr, episodes_out, sums_out, total_steps_out);
+    ENTER(e);
+    rlb_status st = enqueue_range(e, 1, 0, n_episodes, 1, nullptr, episodes_out, sums_out, total_steps_out);
+    rlb_status st2 = finish_pending(e);
+    return st != RLB_OK ? st : st2;
 }
 
 // ------------------------------------------------------------------------------- Policy
 static rlb_status policy_rows(rlb_engine* e, const uint32_t* obs, void* values_out, int which) {
     if (!e || !obs || !values_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     StepArgs a;
     const void* in;
     void* dev;
     CK(stage_in(e, 0, obs, N * 4, &in));
     CK(stage_out(e, 1, values_out, N * e->A * e->real_size, &dev));
-    a.obs = (const uint32_t*)in; a.real_out = dev; a.which = which;
+    a.obs = (const uint32_t*)in; a.real_out = dev; a.which = which; a.any_not_ready = e->d_flagword;
+    CK(flags_clear(e));
     CK(dispatch_step(e, OP_POLICY_ROWS, a));
     CK(finish_out(e, values_out, dev, N * e->A * e->real_size));
-    return RLB_OK;
+    return flags_check(e);
 }
 rlb_status rlb_policy_predict(rlb_engine* e, const uint32_t* obs, void* values_out) { return policy_rows(e, obs, values_out, 0); }
 rlb_status rlb_policy_get_values(rlb_engine* e, const uint32_t* obs, void* values_out) { return policy_rows(e, obs, values_out, 1); }
@@ -888,21 +1066,21 @@ rlb_status rlb_policy_get_values(rlb_engine* e, const uint32_t* obs, void* value
 rlb_status rlb_policy_update(rlb_engine* e, const uint32_t* obs, const uint32_t* action, const uint32_t* next_obs, const void* temporal_difference) {
     (void)next_obs;   // unused by both tabular policies (tabular_policy.rs:35 `_next_obs`)
     if (!e || !obs || !action || !temporal_difference) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     StepArgs a;
     const void* in[3];
     CK(stage_in(e, 0, obs, N * 4, &in[0]));
     CK(stage_in(e, 1, action, N * 4, &in[1]));
     CK(stage_in(e, 2, temporal_difference, N * e->real_size, &in[2]));
-    a.obs = (const uint32_t*)in[0]; a.action = (const uint32_t*)in[1]; a.td_in = in[2];
+    a.obs = (const uint32_t*)in[0]; a.action = (const uint32_t*)in[1]; a.td_in = in[2]; a.any_not_ready = e->d_flagword;
+    CK(flags_clear(e));
     CK(dispatch_step(e, OP_POLICY_UPDATE, a));
-    CK(cudaStreamSynchronize(e->stream));
-    return RLB_OK;
+    return flags_check(e);
 }
 rlb_status rlb_policy_after_update(rlb_engine* e) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     if (e->cfg.policy_kind == RLB_POLICY_DOUBLE) {
         const uint64_t N = e->cfg.n_agents;
         k_flag_flip<<<(unsigned)((N + 255) / 256), 256, 0, e->stream>>>(e->d_flag, N);
@@ -914,7 +1092,7 @@ rlb_status rlb_policy_after_update(rlb_engine* e) {
 // ------------------------------------------------------------------------------- ActionSelection
 rlb_status rlb_selector_get_action(rlb_engine* e, const uint32_t* obs, const void* values, uint32_t* action_out) {
     if (!e || !obs || !values || !action_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     StepArgs a;
     const void* in[2];
@@ -922,15 +1100,15 @@ rlb_status rlb_selector_get_action(rlb_engine* e, const uint32_t* obs, const voi
     CK(stage_in(e, 0, obs, N * 4, &in[0]));
     CK(stage_in(e, 1, values, N * e->A * e->real_size, &in[1]));
     CK(stage_out(e, 2, action_out, N * 4, &dev));
-    a.obs = (const uint32_t*)in[0]; a.values = in[1]; a.u32_out = (uint32_t*)dev;
+    a.obs = (const uint32_t*)in[0]; a.values = in[1]; a.u32_out = (uint32_t*)dev; a.any_not_ready = e->d_flagword;
+    CK(flags_clear(e));
     CK(dispatch_step(e, OP_SELECTOR_GET_ACTION, a));
     CK(finish_out(e, action_out, dev, N * 4));
-    CK(cudaStreamSynchronize(e->stream));
-    return RLB_OK;
+    return flags_check(e);
 }
 rlb_status rlb_selector_get_exploration_probs(rlb_engine* e, const uint32_t* obs, const void* values, void* probs_out) {
     if (!e || !obs || !values || !probs_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     StepArgs a;
     const void* in[2];
@@ -938,15 +1116,15 @@ rlb_status rlb_selector_get_exploration_probs(rlb_engine* e, const uint32_t* obs
     CK(stage_in(e, 0, obs, N * 4, &in[0]));
     CK(stage_in(e, 1, values, N * e->A * e->real_size, &in[1]));
     CK(stage_out(e, 2, probs_out, N * e->A * e->real_size, &dev));
-    a.obs = (const uint32_t*)in[0]; a.values = in[1]; a.real_out = dev;
+    a.obs = (const uint32_t*)in[0]; a.values = in[1]; a.real_out = dev; a.any_not_ready = e->d_flagword;
+    CK(flags_clear(e));
     CK(dispatch_step(e, OP_SELECTOR_PROBS, a));
     CK(finish_out(e, probs_out, dev, N * e->A * e->real_size));
-    CK(cudaStreamSynchronize(e->stream));
-    return RLB_OK;
+    return flags_check(e);
 }
 rlb_status rlb_selector_update(rlb_engine* e) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     if (e->cfg.selector_kind == RLB_SEL_EPS_GREEDY) {
         const uint64_t N = e->cfg.n_agents;
         k_eps_decay<<<(unsigned)((N + 255) / 256), 256, 0, e->stream>>>(e->d_eps, N, e->cfg.decay_kind, e->cfg.epsilon_decay, e->cfg.final_epsilon);
@@ -958,7 +1136,7 @@ rlb_status rlb_selector_update(rlb_engine* e) {
 // ------------------------------------------------------------------------------- snapshots
 rlb_status rlb_download_tables(rlb_engine* e, void* q_out, uint32_t* counts_out) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     if (q_out) {
         const size_t n_el = (size_t)N * e->T * e->S * e->A;
@@ -989,7 +1167,7 @@ rlb_status rlb_download_tables(rlb_engine* e, void* q_out, uint32_t* counts_out)
 
 rlb_status rlb_upload_tables(rlb_engine* e, const void* q, const uint32_t* counts) {
     if (!e) { set_error("engine is NULL"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     if (q) {
         const size_t n_el = (size_t)N * e->T * e->S * e->A;
@@ -1017,7 +1195,7 @@ rlb_status rlb_upload_tables(rlb_engine* e, const void* q, const uint32_t* count
 rlb_status rlb_get_agent_states(rlb_engine* e, rlb_agent_state* states_out) {
     if (!e || !states_out) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
     if (is_device_ptr(states_out)) { set_error("states_out must be a host pointer"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     std::vector<double> eps(N);
     std::vector<uint64_t> t(N), n(N);
@@ -1036,12 +1214,17 @@ rlb_status rlb_get_agent_states(rlb_engine* e, rlb_agent_state* states_out) {
 rlb_status rlb_set_agent_states(rlb_engine* e, const rlb_agent_state* states) {
     if (!e || !states) { set_error("NULL argument"); return RLB_ERR_INVALID_ARG; }
     if (is_device_ptr(states)) { set_error("states must be a host pointer"); return RLB_ERR_INVALID_ARG; }
-    CK(cudaSetDevice(e->cfg.device));
+    ENTER(e);
     const uint64_t N = e->cfg.n_agents;
     std::vector<double> eps(N);
     std::vector<uint64_t> t(N), n(N);
     std::vector<uint8_t> flag(N);
-    for (uint64_t i = 0; i < N; ++i) { eps[i] = states[i].epsilon; t[i] = states[i].ucb_t; n[i] = states[i].rng_n; flag[i] = states[i].policy_flag ? 1 : 0; }
+    for (uint64_t i = 0; i < N; ++i) {
+        eps[i] = states[i].epsilon; t[i] = states[i].ucb_t; n[i] = states[i].rng_n; flag[i] = states[i].policy_flag ? 1 : 0;
+        // every env but Blackjack draws 64-bit values only: its stream position is always even, and the fused kernel
+        // reads aligned pairs (Rng::next_u64<EVEN>)
+        if (e->cfg.env_kind != RLB_ENV_BLACKJACK && (n[i] & 1ull)) { set_error("agent %llu: odd rng_n %llu on an env that only draws 64-bit values", (unsigned long long)i, (unsigned long long)n[i]); return RLB_ERR_INVALID_ARG; }
+    }
     CK(cudaMemcpyAsync(e->d_eps, eps.data(), N * 8, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->d_ucb_t, t.data(), N * 8, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->d_rng_n, n.data(), N * 8, cudaMemcpyHostToDevice, e->stream));

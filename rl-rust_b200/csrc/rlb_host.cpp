@@ -5,9 +5,22 @@
 #include "rlb_taxi_start.h"
 
 #include <cmath>
+#include <cstdarg>
+#include <cstdio>
 #include <cstring>
 
 namespace rlb {
+
+static thread_local std::string g_last_error;
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+const char* last_error_cstr() { return g_last_error.c_str(); }
 
 static inline uint16_t pack_tr(uint32_t s2, uint32_t rcode, bool term) {
     return (uint16_t)(s2 | (rcode << 10) | (term ? 0x8000u : 0u));
@@ -110,17 +123,30 @@ static void build_cliff(EnvTables& t) {
     }
 }
 
-// env/frozen_lake.rs:23-102.  [S][4][3] slots; reward code 1 -> 1.0 (entering G).
+// env/frozen_lake.rs:23-102.  [S][4][3] slots; reward code 1 -> 1.0 (entering G).  `map` is MAP_4X4 (:23), MAP_8X8
+// (:25-28) or the caller's own rows (FrozenLakeEnv::new takes any `&[&str]`, :48).
 static bool build_frozen_lake(const rlb_config& cfg, EnvTables& t, std::string& err) {
-    static const char* k4[4] = {"SFFF", "FHFH", "FFFH", "HFFG"};
-    static const char* k8[8] = {"SFFFFFFF", "FFFFFFFF", "FFFHFFFF", "FFFFFHFF", "FFFHFFFF", "FHHFFFHF", "FHFFHFHF", "FFFHFFFG"};
-    const char* const* map = cfg.map_id == 0 ? k4 : k8;
-    const int n = cfg.map_id == 0 ? 4 : 8;
-    t.S = (uint32_t)(n * n); t.A = 4;
+    static const char* k4 = "SFFF" "FHFH" "FFFH" "HFFG";
+    static const char* k8 = "SFFFFFFF" "FFFFFFFF" "FFFHFFFF" "FFFFFHFF" "FFFHFFFF" "FHHFFFHF" "FHFFHFHF" "FFFHFFFG";
+    int nrow, ncol;
+    std::string map;
+    if (cfg.map_id == RLB_MAP_4X4) { nrow = ncol = 4; map = k4; }
+    else if (cfg.map_id == RLB_MAP_8X8) { nrow = ncol = 8; map = k8; }
+    else if (cfg.map_id == RLB_MAP_CUSTOM) {
+        if (!cfg.map || cfg.map_rows == 0 || cfg.map_cols == 0) { err = "frozen lake: map_id = RLB_MAP_CUSTOM needs map, map_rows, map_cols"; return false; }
+        if ((uint64_t)cfg.map_rows * cfg.map_cols > 1024) { err = "frozen lake: at most 1024 cells"; return false; }
+        nrow = (int)cfg.map_rows; ncol = (int)cfg.map_cols;
+        if (strnlen(cfg.map, (size_t)nrow * ncol + 1) != (size_t)nrow * ncol) { err = "frozen lake: map must hold exactly map_rows * map_cols cells"; return false; }
+        map.assign(cfg.map, (size_t)nrow * ncol);
+        for (char c : map) if (c != 'S' && c != 'F' && c != 'H' && c != 'G') { err = "frozen lake: map cells must be S, F, H or G"; return false; }
+    } else { err = "frozen lake: map_id must be 0 (4x4), 1 (8x8) or 2 (custom)"; return false; }
+    const int n_cells = nrow * ncol;
+    t.S = (uint32_t)n_cells; t.A = 4;
     t.trans.assign((size_t)t.S * 12, 0);
-    for (int s = 0; s < n * n; ++s) {
-        const int row = s / n, col = s % n;
-        const char here = map[row][col];
+    t.dead_cell.assign(t.S, 0);
+    for (int s = 0; s < n_cells; ++s) {
+        const int row = s / ncol, col = s % ncol;
+        const char here = map[s];
         for (int a = 0; a < 4; ++a) {
             uint16_t* slot = &t.trans[((size_t)s * 4 + a) * 3];
             if (here == 'G' || here == 'H') { slot[0] = pack_tr((uint32_t)s, 0, true); t.dead_cell[s] = 1; continue; }   // :75-76, never stepped from
@@ -128,9 +154,9 @@ static bool build_frozen_lake(const rlb_config& cfg, EnvTables& t, std::string& 
             const int n_slots = cfg.slippery ? 3 : 1;
             for (int i = 0; i < n_slots; ++i) {
                 int r2 = row, c2 = col;
-                grid_move(n, n, r2, c2, cfg.slippery ? cand[i] : a);
-                const char c = map[r2][c2];
-                slot[i] = pack_tr((uint32_t)(r2 * n + c2), c == 'G' ? 1u : 0u, c == 'G' || c == 'H');
+                grid_move(nrow, ncol, r2, c2, cfg.slippery ? cand[i] : a);
+                const char c = map[r2 * ncol + c2];
+                slot[i] = pack_tr((uint32_t)(r2 * ncol + c2), c == 'G' ? 1u : 0u, c == 'G' || c == 'H');
             }
         }
     }
@@ -140,7 +166,25 @@ static bool build_frozen_lake(const rlb_config& cfg, EnvTables& t, std::string& 
     if (b3 < 1.0) { err = "frozen lake: slip distribution does not reach 1.0"; return false; }
     t.slip_thr0 = k_threshold(b1);
     t.slip_thr1 = k_threshold(b2);
-    // start distribution: both maps have one 'S' at index 0 -> reset() always yields 0 after one draw (:106-113)
+    // start distribution (:54-66): 1/count on every 'S' cell; reset() walks the running f64 sum over all cells
+    // (:106-109, utils.rs:33-43) — the first 'S' whose cumulative exceeds the draw, cell 0 if none does (also the
+    // answer for a map without 'S': the distribution is all zeros).
+    int count = 0;
+    for (char c : map) count += c == 'S';
+    t.thr.clear(); t.thr_state.clear();
+    const double each = count ? 1.0 / (double)count : 0.0;
+    double running = 0.0;
+    for (int s = 0; s < n_cells; ++s) {
+        if (map[s] != 'S') continue;
+        running += each;
+        t.thr.push_back(k_threshold(running));
+        t.thr_state.push_back((uint16_t)s);
+    }
+    t.fl_start = 0;
+    if (count == 1) {   // one start cell: cumulative 1.0 exceeds every draw
+        t.fl_start = t.thr_state[0];
+        t.thr.clear(); t.thr_state.clear();
+    }
     return true;
 }
 
@@ -166,7 +210,6 @@ bool build_env_tables(const rlb_config& cfg, EnvTables& t, std::string& err) {
     switch (cfg.env_kind) {
         case RLB_ENV_BLACKJACK: t.S = 1456; t.A = 2; t.n_live = t.S; std::memset(t.row_lut, 0xFF, sizeof t.row_lut); return true;
         case RLB_ENV_FROZEN_LAKE:
-            if (cfg.map_id != 0 && cfg.map_id != 1) { err = "frozen lake: map_id must be 0 (4x4) or 1 (8x8)"; return false; }
             if (!build_frozen_lake(cfg, t, err)) return false;
             build_row_lut(cfg, t);
             return true;

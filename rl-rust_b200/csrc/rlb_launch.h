@@ -26,16 +26,18 @@ struct StepArgs {   // device pointers for the step-level kernels
     const void* td_in = nullptr;
     void* real_out = nullptr;
     uint32_t* u32_out = nullptr;
+    uint32_t* u32_out2 = nullptr;
     double* reward_out = nullptr;
     uint8_t* term_out = nullptr;
+    uint8_t* kind_out = nullptr;
     uint8_t* not_ready_out = nullptr;
-    uint32_t* any_not_ready = nullptr;
+    uint32_t* any_not_ready = nullptr;   // the engine's flag word (FLAG_* bits, rlb_step_kernels.cuh)
     int which = 0;
 };
 
 enum StepOp {
     OP_ENV_CONSTRUCT, OP_ENV_RESET, OP_ENV_STEP, OP_GET_ACTION, OP_UPDATE, OP_POLICY_ROWS, OP_POLICY_UPDATE,
-    OP_SELECTOR_GET_ACTION, OP_SELECTOR_PROBS
+    OP_SELECTOR_GET_ACTION, OP_SELECTOR_PROBS, OP_AGENT_STEP
 };
 
 template <int ENV> cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStream_t stream);

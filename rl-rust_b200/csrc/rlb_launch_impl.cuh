@@ -165,38 +165,45 @@ cudaError_t launch_step(StepOp op, const Variant& v, const DevParams& p, const S
             k_env_step<ENV><<<grid, kBlock, smem, stream>>>(p, a.action, a.u32_out, a.reward_out, a.term_out, a.not_ready_out, a.any_not_ready);
             break;
         case OP_GET_ACTION: {
-#define RLB_CALL(R, P, S, T) k_get_action<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.u32_out)
+#define RLB_CALL(R, P, S, T) k_get_action<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.u32_out, a.any_not_ready)
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
             break;
         }
         case OP_UPDATE: {
 #define RLB_CALL(R, P, S, T) \
-    k_update<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.action, a.reward, a.term, a.obs2, a.action2, (R*)a.real_out)
+    k_update<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.action, a.reward, a.term, a.obs2, a.action2, (R*)a.real_out, a.any_not_ready)
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
             break;
         }
         case OP_POLICY_ROWS: {
-#define RLB_CALL(R, P, S, T) k_policy_rows<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (R*)a.real_out, a.which)
+#define RLB_CALL(R, P, S, T) k_policy_rows<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (R*)a.real_out, a.which, a.any_not_ready)
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
             break;
         }
         case OP_POLICY_UPDATE: {
-#define RLB_CALL(R, P, S, T) k_policy_update<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.action, (const R*)a.td_in)
+#define RLB_CALL(R, P, S, T) k_policy_update<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, a.action, (const R*)a.td_in, a.any_not_ready)
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
             break;
         }
         case OP_SELECTOR_GET_ACTION: {
-#define RLB_CALL(R, P, S, T) k_selector_get_action<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (const R*)a.values, a.u32_out)
+#define RLB_CALL(R, P, S, T) k_selector_get_action<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (const R*)a.values, a.u32_out, a.any_not_ready)
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
             break;
         }
         case OP_SELECTOR_PROBS: {
-#define RLB_CALL(R, P, S, T) k_selector_probs<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (const R*)a.values, (R*)a.real_out)
+#define RLB_CALL(R, P, S, T) k_selector_probs<ENV, R, P, S, T><<<grid, kBlock, 0, stream>>>(p, a.obs, (const R*)a.values, (R*)a.real_out, a.any_not_ready)
+            RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+            break;
+        }
+        case OP_AGENT_STEP: {
+#define RLB_CALL(R, P, S, T) \
+    k_agent_step<ENV, R, P, S, T><<<grid, kBlock, smem, stream>>>(p, a.kind_out, a.u32_out, a.u32_out2, a.reward_out, a.term_out, (R*)a.real_out)
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
             break;

@@ -7,14 +7,11 @@ import numpy as np
 
 from oracle import oracle_py as O
 
-ENV_NAMES = {0: "blackjack", 1: "frozen_lake", 2: "cliff_walking", 3: "taxi"}
-TARGET_NAMES = {0: "sarsa", 1: "qlearning", 2: "expected_sarsa"}
+import importlib as _il
 
-
-def combo_id(c):
-    return "%s-%s-%s-%s-%s-%s" % (ENV_NAMES[c["env"]], "traces" if c["agent"] else "onestep",
-                                  "ucb" if c["selector"] else "eps", "double" if c["policy"] else "basic",
-                                  TARGET_NAMES[c["target"]], "f64" if c["real"] else "f32")
+_W = _il.import_module("rl-rust_b200.workloads")   # product-side helpers: the CLI defaults and engine construction
+ENV_NAMES, TARGET_NAMES = _W.ENV_NAMES, _W.TARGET_NAMES
+combo_id, hyper, make_engine = _W.combo_id, _W.hyper, _W.make_engine
 
 
 def all_combos(envs=(0, 1, 2, 3), agents=(0, 1), selectors=(0, 1), policies=(0, 1), targets=(0, 1, 2), reals=(0, 1)):
@@ -24,31 +21,13 @@ def all_combos(envs=(0, 1, 2, 3), agents=(0, 1), selectors=(0, 1), policies=(0, 
     return out
 
 
-def hyper(n_episodes, **over):
-    """The reference CLI's defaults (bin/taxi.rs:22-68) with the decay derived from n_episodes (:78)."""
-    h = dict(map_id=1, slippery=True, max_steps=100, lr=0.05, gamma=0.95, lambda_=0.5, eps0=1.0,
-             eps_decay=1.0 / (0.5 * n_episodes), eps_final=0.0, ucb_c=0.5, default_q=0.0, decay_kind=0, seed=0x5EED0001, planning_steps=0)
-    h.update(over)
-    return h
-
-
 def oracle_config(c, h):
     return O.make_config(c["env"], map_id=h["map_id"], slippery=h["slippery"], max_steps=h["max_steps"],
                          policy=c["policy"], selector=c["selector"], target=c["target"], agent=c["agent"],
                          real=c["real"], decay_kind=h["decay_kind"], lr=h["lr"], gamma=h["gamma"],
                          lambda_=h["lambda_"], eps0=h["eps0"], eps_decay=h["eps_decay"], eps_final=h["eps_final"],
                          ucb_c=h["ucb_c"], default_q=h["default_q"], seed=h["seed"],
-                         planning_steps=h.get("planning_steps", 0))
-
-
-def make_engine(c, h, n_agents, first_agent_id=0, **kw):
-    rlb = importlib.import_module("rl-rust_b200")
-    return rlb.Engine(c["env"], n_agents=n_agents, map_id=h["map_id"], slippery=h["slippery"], max_steps=h["max_steps"],
-                      policy=c["policy"], selector=c["selector"], target=c["target"], agent=c["agent"], real=c["real"],
-                      decay_kind=h["decay_kind"], learning_rate=h["lr"], discount_factor=h["gamma"],
-                      lambda_factor=h["lambda_"], initial_epsilon=h["eps0"], epsilon_decay=h["eps_decay"],
-                      final_epsilon=h["eps_final"], confidence_level=h["ucb_c"], default_value=h["default_q"],
-                      seed=h["seed"], first_agent_id=first_agent_id, planning_steps=h.get("planning_steps", 0), **kw)
+                         planning_steps=h.get("planning_steps", 0), map_rows=h.get("map_rows"))
 
 
 def bits_equal(a, b):

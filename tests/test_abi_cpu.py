@@ -16,12 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(rlb):
     hdr = open(os.path.join(ROOT, "include", "rlb.h")).read()
-    declared = set(re.findall(r"^(?:rlb_status|void|int|const char\*|uint32_t|uint64_t|double)\s+(rlb_[a-z0-9_]+)\(", hdr, re.M))
+    declared = set(re.findall(r"^(?:rlb_status|void|int|int32_t|const char\*|uint32_t|uint64_t|double)\s+(rlb_[a-z0-9_]+)\(", hdr, re.M))
     assert len(declared) >= 40
     assert declared == set(rlb.abi.EXPORTS), declared ^ set(rlb.abi.EXPORTS)
     for sym in declared:
         assert hasattr(rlb.abi.lib, sym), sym
-    assert rlb.abi.lib.rlb_abi_version() == 1
+    assert rlb.abi.lib.rlb_abi_version() == 2
 
 
 def test_struct_layouts_match_header(rlb):
