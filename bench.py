@@ -15,9 +15,15 @@ e2e     = the same through the C ABI with HOST buffers: the per-agent episode re
           (reward_history / episode_length of agent.rs:117) and the per-episode sums are
           copied to pinned host memory inside the timed region.
 
-Default workload = BASELINE.json configs[1] ("c2"): FrozenLake 8x8 slippery, Sarsa(lambda),
-eps-greedy, Basic, 1 048 576 agents per GPU (weak scaling), f32.  `--workload c4` is the Taxi
-Q-learning target configuration (2 097 152 agents per GPU = 16 M over 8 GPUs).
+The headline line is BASELINE.json configs[1] ("c2"): FrozenLake 8x8 slippery, Sarsa(lambda),
+eps-greedy, Basic, 1 048 576 agents per GPU (weak scaling), f32.  The same JSON line carries
+`workloads`: full sub-records (value, e2e, roofline, clocks, config) of
+  c4      Taxi one-step Q-learning, eps-greedy — the configuration north_star's 1e11 target is
+          stated on: 16 777 216 agents SHARDED over the GPUs (strong scaling; on one GPU the
+          2 097 152-agent shard of the 8-GPU job, 16 M agents do not fit 180 GB),
+  c3      CliffWalking Expected Sarsa, Double, UCB, 4 194 304 agents per GPU,
+  c2_f64  the headline configuration in the reference's own arithmetic (f64).
+`--workload X` measures one configuration alone; `--sub ''` drops the sub-records.
 
 `--impl reference` times the CPU oracle (the reference cannot be compiled here: no Rust
 toolchain) on the host cores, on a bounded sample of the same workload.
@@ -35,45 +41,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-WORKLOADS = {
-    "c1": dict(desc="Blackjack one-step Q-learning, eps-greedy, Basic", env=0, agent=0, selector=0, policy=0, target=1,
-               agents_per_gpu=1 << 22, n_episodes=1000, chunk=100),
-    "c2": dict(desc="FrozenLake 8x8 slippery, Sarsa(lambda) eligibility traces, eps-greedy, Basic", env=1, agent=1,
-               selector=0, policy=0, target=0, agents_per_gpu=1 << 20, n_episodes=1000, chunk=100, slippery=True),
-    "c3": dict(desc="CliffWalking Expected Sarsa, Double policy, UCB", env=2, agent=0, selector=1, policy=1, target=2,
-               agents_per_gpu=1 << 22, n_episodes=200, chunk=20),
-    "c4": dict(desc="Taxi one-step Q-learning, eps-greedy, Basic", env=3, agent=0, selector=0, policy=0, target=1,
-               agents_per_gpu=1 << 21, n_episodes=1000, chunk=100),
-}
-# not a BASELINE config: the crate's Dyna bin (src/bin/cliffwalking_model.rs), "next" row N4 of SURVEY.md §8(f)
-WORKLOADS["dyna"] = dict(desc="CliffWalking one-step Dyna-Q (InternalModelAgent, RandomModel, 10 planning steps), eps-greedy, Basic",
-                         env=2, agent=0, selector=0, policy=0, target=1, planning_steps=10, agents_per_gpu=1 << 20, n_episodes=200,
-                         chunk=20)
-# C5, the full sweep: 4 envs x {Sarsa, Q, Expected Sarsa one-step; Sarsa(lambda), Q(lambda)} x {eps-greedy, UCB} x
-# {Basic, Double} = 80 cells, every cell an engine of its own on every GPU, one metric gather per cell per step.
-WORKLOADS["c5"] = dict(desc="full sweep: 4 envs x 5 update rules x {eps-greedy, UCB} x {Basic, Double} = 80 cells", cells=[
-    dict(env=env, agent=agent, target=target, selector=sel, policy=pol, slippery=True)
-    for env in (0, 1, 2, 3) for (agent, target) in ((0, 0), (0, 1), (0, 2), (1, 0), (1, 1)) for sel in (0, 1) for pol in (0, 1)],
-    agents_per_gpu=8192, n_episodes=1000, chunk=100)
-A_OF_ENV = {0: 2, 1: 4, 2: 4, 3: 6}
-
-
-def algorithmic_bytes(w, real_size, train_steps, trace_rows):
-    """bytes the algorithm must move per agent-step between the table store and the SM.
-    one-step Basic: read Q[s'][0..A) + read Q[s][a] + write Q[s][a] + 2 B packed transition = (A+2)*R + 2;
-    Double: (2A+3)*R + 2; UCB adds 4A (counts row) + 8 (count RMW); traces add 4*R*A per swept row
-    (read e, read Q, write Q, write e)."""
-    A, R = A_OF_ENV[w["env"]], real_size
-    per_step = ((2 * A + 3) * R + 2) if w["policy"] else ((A + 2) * R + 2)
-    if w["selector"]:
-        per_step += 4 * A + 8
-    k = w.get("planning_steps", 0)
-    if k:   # Dyna: membership word + k replays, each one 8-byte model entry and one more update
-        per_step = per_step * (1 + k) + 8 * k + 4
-    return train_steps * per_step + trace_rows * 4 * R * A
+def _workloads():
+    return importlib.import_module("rl-rust_b200.workloads")
 
 
 class ClockSampler:
@@ -123,45 +94,43 @@ class ClockSampler:
         return out
 
 
-def peaks():
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return 6650.0, 1965.0, "fallback (B200_PROFILING.md: 6.65 TB/s, 1965 MHz)"
 
 
-def measured_traffic(workload, agents_per_gpu, dtype):
-    """dram__bytes_read.sum + dram__bytes_write.sum per k_run launch from the committed ncu capture of this exact
-    configuration (profiles/traffic.json); None when the run's configuration was not captured."""
+def kernel_counters(name, dtype, agents_per_gpu):
+    """Per-env-step warp instructions and DRAM bytes of k_run for this configuration, from the committed ncu captures
+    (profiles/counters.json, written by tools/make_counters.py from the ncu CSVs named there).  Counters taken at
+    another agent count of the same configuration are used as per-step figures and flagged."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(workload)
-        if t and t["agents_per_gpu"] == agents_per_gpu and t["dtype"] == dtype:
-            return t["dram_bytes_per_launch"]
+        with open(os.path.join(ROOT, "profiles", "counters.json")) as f:
+            table = json.load(f)["kernels"]
     except Exception:
-        pass
+        return None
+    exact = [t for t in table if t["workload"] == name and t["dtype"] == dtype and t["agents_per_gpu"] == agents_per_gpu]
+    near = [t for t in table if t["workload"] == name and t["dtype"] == dtype]
+    if exact:
+        return dict(exact[-1], exact_size=True)
+    if near:
+        return dict(near[-1], exact_size=False)
     return None
-
-
-def workload_hyper(w):
-    import parity as P
-    return P.hyper(w["n_episodes"], slippery=w.get("slippery", False), planning_steps=w.get("planning_steps", 0))
-
-
-def combo(w, real):
-    return dict(env=w["env"], agent=w["agent"], selector=w["selector"], policy=w["policy"], target=w["target"], real=real)
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
 def cpu_sample(w, real, n_agents, n_threads, chunk_begin, chunk_end, sessions=None):
     """Advance `n_agents` oracle sessions by episodes [chunk_begin, chunk_end) on `n_threads` host threads.
-    Returns (train_steps, seconds, sessions)."""
+    Returns (train_steps, seconds, sessions).  The one place bench.py touches oracle/ (the CPU baseline)."""
+    W = _workloads()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import parity as P
     from oracle import oracle_py as O
     from concurrent.futures import ThreadPoolExecutor
-    h = workload_hyper(w)
-    cfg = P.oracle_config(combo(w, real), h)
+    cfg = P.oracle_config(W.combo(w, real), W.workload_hyper(w))
     if sessions is None:
         sessions = [O.Session(cfg, i) for i in range(n_agents)]
     L = O.lib()
@@ -182,7 +151,7 @@ def cpu_sample(w, real, n_agents, n_threads, chunk_begin, chunk_end, sessions=No
     return int(sum(int(l.sum()) for l in lens)), dt, sessions
 
 
-def run_reference_arm(args, w, real):
+def run_reference_arm(args, name, w, real):
     """`--impl reference`: the reference's CPU implementation of the path.  The Rust crate cannot be built in this
     image, so the C++ oracle (oracle/, a line-by-line port with hash-map tables and the per-step allocations the
     reference makes) stands in, one independent agent stream per host thread."""
@@ -215,7 +184,7 @@ def run_reference_arm(args, w, real):
         "impl": "reference", "metric": "agent-env steps/sec (updates incl.)", "value": v, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if real else "f32", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + w["desc"], "agents": n_agents * len(cells), "episodes_per_step": chunk,
+        "config": {"workload": name + ": " + w["desc"], "agents": n_agents * len(cells), "episodes_per_step": chunk,
                    "n_episodes": n_ep, "eval_at": n_ep // 10},
         "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                          "sample": "%d agents (%d per host thread%s) x %d-episode chunks of the same run; C++ oracle, hash-map tables"
@@ -226,219 +195,320 @@ def run_reference_arm(args, w, real):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+class Job:
+    """torch.distributed plumbing of one bench process (rank) plus the library's NCCL communicator."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.sh = importlib.import_module("rl-rust_b200.sharding")
+        self.comm = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.comm = self.sh.make_comm(self.local_rank)   # the library's own communicator (rlb_comm_*), used for the path's gather
+        self.stream = torch.cuda.current_stream()
+        self.props = torch.cuda.get_device_properties(self.local_rank)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allreduce(self, vals, op):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_streams):
+    """One configuration on this job's GPUs: W warm-up steps, K timed steps (device value), the e2e leg, the CPU
+    baseline sample.  Returns the record (rank 0) or None."""
+    torch = job.torch
+    W = _workloads()
+    rlb = importlib.import_module("rl-rust_b200")
+    world, rank = job.world, job.rank
+    real_size = 4 if real == 0 else 8
+    dtype = "f32" if real == 0 else "f64"
+    # Sharding: a workload with `agents_total` is ONE job of that many agents cut into contiguous shards of global ids
+    # (strong scaling); the others run `agents_per_gpu` agents on every GPU (weak scaling).  Either way the Philox counter
+    # carries the global id, so every agent's results are independent of the number of GPUs.
+    strong = "agents_total" in w and world > 1 and not args.agents_per_gpu
+    if strong:
+        first_id, N = job.sh.shard_sizes(w["agents_total"], world)[rank]
+    else:
+        N = args.agents_per_gpu or w["agents_per_gpu"]
+        first_id = job.sh.shard(rank, N)
+    chunk, n_ep = w["chunk"], w["n_episodes"]
+    eval_at = max(1, n_ep // 10)
+    chunks_per_run = n_ep // chunk
+    cells = [dict(w, **c) for c in w["cells"]] if "cells" in w else [w]
+    stream = job.stream
+    n_groups = max(1, min(cell_streams, len(cells))) if len(cells) > 1 else 1
+    group_streams = [stream] if n_groups == 1 else [torch.cuda.Stream() for _ in range(n_groups)]
+    engines = []
+    for ci, cell in enumerate(cells):
+        e_ = W.make_engine(W.combo(cell, real), W.workload_hyper(cell), N, first_agent_id=first_id, device=job.local_rank, store_kind=args.store)
+        e_.set_stream(group_streams[ci % n_groups].cuda_stream)
+        engines.append(e_)
+    eng = engines[0]
+    table_bytes = sum(N * e_.S * e_.T * e_.A * real_size for e_ in engines)   # every env's rows are unpadded (Taxi: 24-byte f32 rows)
+
+    sums_dev = [torch.zeros((chunk, 4), dtype=torch.float64, device="cuda") for _ in cells]
+    gathered = [torch.zeros((world, chunk, 4), dtype=torch.float64, device="cuda") for _ in cells] if (world > 1 and rank == 0) else None
+    rec_size = 16 if real == 0 else 32
+    state = {"k": 0}
+    acc = {}
+
+    def reset_acc():
+        acc.update(train_steps=0, eval_steps=0, kernel_ms=0.0, launches=0, trace_rows=0, alg_bytes=0)
+
+    def account(ci, r):
+        acc["train_steps"] += r["train_steps"]; acc["eval_steps"] += r["eval_steps"]
+        acc["kernel_ms"] += r["kernel_ms"]; acc["launches"] += 2 * r["kernel_launches"]   # each k_run is followed by one k_episode_sums
+        acc["trace_rows"] += r["trace_rows"]
+        acc["alg_bytes"] += W.algorithmic_bytes(cells[ci], real_size, r["train_steps"], r["trace_rows"])
+
+    def step(host=None, wait=True, count=True):
+        """One step of every cell: enqueue (asynchronous train call; cells on different streams overlap), then wait.
+        host = None: outputs stay in HBM (device leg).  host = (sums, records, gathered): pinned host buffers (e2e leg);
+        with wait=False the tail of this step's record copy overlaps the next step's kernels and the results are
+        accounted when the library reports the call complete (drain)."""
+        k = state["k"]
+        c = k % chunks_per_run
+        for ci, e_ in enumerate(engines):
+            if c == 0 and k > 0:
+                e_.agent_reset()                                # src/bin/taxi.rs:200
+            sums_target = sums_dev[ci] if (host is None or world > 1) else host[0][ci]
+            rec_target = None if host is None else host[1][ci][k & 1]
+            e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=sums_target, episodes_out=rec_target, wait=False)
+            if world > 1:                                       # the path's one collective: per-episode metrics to rank 0 (rlb_comm, NCCL)
+                s_ = group_streams[ci % n_groups]
+                job.sh.gather_episode_sums(sums_dev[ci], comm=job.comm, out=gathered[ci] if rank == 0 else None, stream=s_.cuda_stream)
+                if host is not None and rank == 0:              # e2e: the gathered curves land in rank 0's host memory
+                    with torch.cuda.stream(s_):
+                        host[2][ci].copy_(gathered[ci], non_blocking=True)
+        if wait:
+            drain(count)
+        state["k"] = k + 1
+
+    def drain(count=True):
+        for ci, e_ in enumerate(engines):
+            for r in e_.train_wait():
+                if count:
+                    account(ci, r)
+
+    reset_acc()
+    for _ in range(warmup):
+        step(count=False)
+    # Timing rules: a run that saw a hardware / thermal slowdown is rejected and measured once more (sw_power_cap is
+    # kept and noted in `clocks.reasons`).  Every rank must take the same decision, so the flag is max-reduced.
+    remeasured = False
+    for attempt in range(2):
+        reset_acc()
+        sampler = ClockSampler(job.local_rank)
+        sampler.start()
+        job.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        ev0.record(stream)
+        for _ in range(steps):
+            step()
+        for s_ in group_streams[1:] if n_groups > 1 else []:
+            stream.wait_stream(s_)
+        ev1.record(stream)
+        job.barrier()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop()
+        ms = ev0.elapsed_time(ev1)
+        slowed = float(any(r in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown") for r in clocks.get("reasons", [])))
+        slowed = job.allreduce([slowed], "max")[0]
+        if not slowed or attempt == 1:
+            break
+        remeasured = True
+    clocks["remeasured_after_slowdown"] = remeasured
+    dev = dict(acc)
+
+    # ---- e2e leg: same steps through the asynchronous C-ABI call with pinned HOST buffers; two record buffers per cell
+    # take turns (step k fills buffer k & 1 while the host may still be reading the other)
+    e2e = None
+    if with_e2e:
+        rec_bytes = chunk * N * rec_size
+        double_buf = rec_bytes * len(cells) <= 6e9              # beyond that ONE pinned buffer and synchronous steps (no overlap claimed)
+        host_sums = [torch.zeros((chunk, 4), dtype=torch.float64).pin_memory() for _ in cells]
+        host_recs = []
+        for _ in cells:
+            b0 = torch.zeros((chunk, N, rec_size // 4), dtype=torch.int32).pin_memory()
+            host_recs.append([b0, torch.zeros_like(b0).pin_memory() if double_buf else b0])
+        host_gath = [torch.zeros((world, chunk, 4), dtype=torch.float64).pin_memory() for _ in cells] if (world > 1 and rank == 0) else None
+        reset_acc()
+        job.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step(host=(host_sums, host_recs, host_gath), wait=not double_buf)
+        drain(count=True)                                       # the last call's records are on the host when this returns
+        for s_ in group_streams[1:] if n_groups > 1 else []:
+            stream.wait_stream(s_)
+        e1.record(stream)
+        job.barrier()
+        e2e = {"ms": e0.elapsed_time(e1), "train_steps": acc["train_steps"],
+               "d2h": len(cells) * (rec_bytes + chunk * 32 + 64) + (len(cells) * world * chunk * 32 if (world > 1 and rank == 0) else 0),
+               "h2d": 24 * len(cells), "double_buf": double_buf}
+        del host_recs
+
+    # ---- reduce over ranks: max time, sum of units
+    ms_max, e2e_ms_max, kernel_ms_max = job.allreduce([ms, e2e["ms"] if e2e else 0.0, dev["kernel_ms"]], "max")
+    train_steps, eval_steps, e2e_steps, trace_rows, agents_total = job.allreduce(
+        [dev["train_steps"], dev["eval_steps"], e2e["train_steps"] if e2e else 0, dev["trace_rows"], N * len(cells)], "sum")
+    store = {1: "hbm", 2: "shared_memory_groups", 3: "hybrid_smem_q_l2_traces"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)]
+    for e_ in engines:
+        e_.close()
+    if rank != 0:
+        return None
+
+    value = train_steps / (ms_max * 1e-3)
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    n_sm = job.props.multi_processor_count
+    sm_hz = 1e6 * (clocks.get("sm_mhz") or sm_max_mhz)          # median SM clock sampled during the timed region
+    issue_peak = n_sm * 4 * sm_hz                               # warp-instructions / s: 4 schedulers per SM, one issue per clock
+    smem_peak = n_sm * 128 * sm_hz                              # bytes / s: 128 B per SM per clock
+    n_launch = max(1, dev["launches"] // 2)                     # k_run launches on this rank (each followed by one k_episode_sums)
+    kernel_s = dev["kernel_ms"] * 1e-3
+    env_steps_rank = dev["train_steps"] + dev["eval_steps"]     # this rank's env transitions inside those launches
+    cnt = kernel_counters(name, dtype, N) if len(cells) == 1 else None
+    smem_frac = dev["alg_bytes"] / kernel_s / smem_peak if kernel_s > 0 else None
+    issue_frac = hbm_frac = traffic = inst_per_launch = None
+    if cnt and kernel_s > 0:
+        inst_per_launch = cnt["warp_inst_per_env_step"] * env_steps_rank / n_launch
+        traffic = cnt["dram_bytes_per_env_step"] * env_steps_rank / n_launch
+        issue_frac = inst_per_launch * n_launch / kernel_s / issue_peak
+        hbm_frac = traffic * n_launch / kernel_s / (hbm_peak * 1e9)
+    # the binding resource is the one closest to its peak; these kernels live on chip, so it is instruction issue
+    fracs = {"sm_issue": issue_frac, "smem": smem_frac, "hbm": hbm_frac}
+    bound = max((k for k in fracs if fracs[k] is not None), key=lambda k: fracs[k])
+    if bound == "sm_issue":
+        achieved, peak, unit = inst_per_launch * n_launch / kernel_s, issue_peak, "warp-inst/s"
+    elif bound == "smem":
+        achieved, peak, unit = dev["alg_bytes"] / kernel_s / 1e9, smem_peak / 1e9, "GB/s"
+    else:
+        achieved, peak, unit = traffic * n_launch / kernel_s / 1e9, hbm_peak, "GB/s"
+    rec = {
+        "metric": "agent-env steps/sec (updates incl.)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_max / max(1, steps), "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": name + ": " + w["desc"], "agents_per_gpu": N * len(cells), "agents_total": int(agents_total), "cells": len(cells),
+                   "episodes_per_step": chunk, "n_episodes": n_ep, "eval_at": eval_at, "table_store": store,
+                   "train_steps_timed": train_steps, "eval_steps_executed_not_counted": eval_steps, "env_steps_per_s_incl_eval": (train_steps + eval_steps) / (ms_max * 1e-3),
+                   "l2": "inputs larger than L2: %.2f GB of per-agent tables per GPU vs 126 MB L2 (no flush needed)" % (table_bytes / 1e9),
+                   "parallelism": ("%d agents sharded over %d GPUs by global id (strong scaling)" % (agents_total, world) if strong
+                                   else "agents sharded by global id, %d per GPU (weak scaling)" % N)
+                                  + "; one NCCL gather (rlb_comm_gather_episode_sums, ncclSend/ncclRecv) of [episodes,4] metrics per step"
+                                  + ("; the %d cells' engines spread over %d CUDA streams by one host thread (asynchronous train calls: their "
+                                     "launches overlap, so kernel_share_of_step counts concurrent kernels)" % (len(cells), n_groups) if n_groups > 1 else ""),
+                   "wall_s": t_wall},
+        "clocks": clocks,
+        "gpu_launches": int(dev["launches"]),
+        "roofline": {"bound": bound, "kernel": "k_run", "achieved": achieved, "peak": peak, "unit": unit, "frac": fracs[bound],
+                     "issue_frac": issue_frac, "smem_frac": smem_frac, "hbm_frac": hbm_frac, "traffic": traffic,
+                     "peaks": {"sm_issue_warp_inst_per_s": issue_peak, "smem_gb_s": smem_peak / 1e9, "hbm_gb_s": hbm_peak, "n_sm": n_sm,
+                               "sm_mhz_used": sm_hz / 1e6, "source": peak_src + "; SM count from the device, SM clock = median sampled during the timed region"},
+                     "warp_inst_per_launch": inst_per_launch, "algorithmic_smem_bytes_per_launch": dev["alg_bytes"] / n_launch,
+                     "launch_ms": dev["kernel_ms"] / n_launch, "kernel_share_of_step": dev["kernel_ms"] / ms if ms > 0 else None,
+                     "counters": ({k: cnt[k] for k in ("warp_inst_per_env_step", "dram_bytes_per_env_step", "source", "exact_size", "agents_per_gpu")} if cnt else None),
+                     "note": "issue_frac = warp instructions (committed ncu capture, per env step) / launch time (CUDA events, this run) / "
+                             "(SMs x 4 x clock); smem_frac = SURVEY 8(d) algorithmic bytes / launch time / (SMs x 128 B x clock); "
+                             "hbm_frac = ncu dram bytes / launch time / measured HBM copy bandwidth"},
+    }
+    if e2e:
+        rec["e2e"] = {"value": e2e_steps / (e2e_ms_max * 1e-3), "unit": "agent-steps/s",
+                      "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                      "note": "C-ABI rlb_agent_train_range_async with pinned HOST buffers: per-agent episode records + per-episode sums copied "
+                              "device->host every step (%s; the last copy is waited for inside the timed region); the path has no per-step "
+                              "host inputs besides the call's scalar arguments" % ("two host record buffers take turns" if e2e["double_buf"] else "one host record buffer, every step waited for")}
+    if world == 1 and cpu_agents:
+        ts, dt = 0, 0.0
+        for cell in cells:
+            ts_, dt_, _ = cpu_sample(cell, real, cpu_agents, 1, 0, n_ep)
+            ts += ts_; dt += dt_
+        rec["cpu_baseline"] = {"value": ts / dt, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+                               "sample": "%d agents%s x one full %d-episode run (eval_at %d), C++ oracle single thread, %.1f s"
+                                         % (cpu_agents, " per cell" if len(cells) > 1 else "", n_ep, eval_at, dt)}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "dyna"])
     ap.add_argument("--agents-per-gpu", type=int, default=0)
     ap.add_argument("--real", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--store", type=int, default=0, help="table store: 0 auto, 1 HBM, 2 shared memory")
     ap.add_argument("--cell-streams", type=int, default=8,
-                    help="multi-cell workloads (c5): host threads / CUDA streams the cells' engines are spread over, so that "
-                         "launches too small to fill the GPU overlap (1 = back to back on one stream)")
+                    help="multi-cell workloads (c5): CUDA streams the cells' engines are spread over, so that launches too small to "
+                         "fill the GPU overlap (1 = back to back on one stream)")
+    ap.add_argument("--sub", default=None,
+                    help="comma-separated sub-records to add under `workloads` (c4, c3, c2_f64, c1, c5, dyna); default: "
+                         "'c4,c3,c2_f64' for the default headline run, none when --workload / --agents-per-gpu / --real is given")
+    ap.add_argument("--sub-steps", type=int, default=5)
+    ap.add_argument("--sub-warmup", type=int, default=3)
     args = ap.parse_args()
-    w = dict(WORKLOADS[args.workload])
-    if args.agents_per_gpu:
-        w["agents_per_gpu"] = args.agents_per_gpu
+    W = _workloads()
+    w = dict(W.WORKLOADS[args.workload])
     real = 0 if args.real == "f32" else 1
-    real_size = 4 if real == 0 else 8
     if args.warmup < 3 and args.impl == "ours":
         print("note: --warmup %d < 3 (timing rules ask for >= 3)" % args.warmup, file=sys.stderr)
 
     if args.impl == "reference":
-        run_reference_arm(args, w, real)
+        run_reference_arm(args, args.workload, w, real)
         return
 
     import torch
-    import torch.distributed as dist
-    import parity as P
     rlb = importlib.import_module("rl-rust_b200")
-    sh = importlib.import_module("rl-rust_b200.sharding")
     if not torch.cuda.is_available() or rlb.abi.lib.rlb_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
+    default_run = args.workload == "c2" and not args.agents_per_gpu and args.real == "f32" and args.store == 0
+    subs = args.sub if args.sub is not None else ("c4,c3,c2_f64" if default_run else "")
+    subs = [s for s in subs.split(",") if s]
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    N = w["agents_per_gpu"]
-    chunk, n_ep = w["chunk"], w["n_episodes"]
-    eval_at = max(1, n_ep // 10)
-    chunks_per_run = n_ep // chunk
-    # one engine per cell (N agents each on this GPU); every workload but C5 is a single cell
-    cells = [dict(w, **c) for c in w["cells"]] if "cells" in w else [w]
-    stream = torch.cuda.current_stream()
-    n_groups = max(1, min(args.cell_streams, len(cells))) if len(cells) > 1 else 1
-    group_streams = [stream] if n_groups == 1 else [torch.cuda.Stream() for _ in range(n_groups)]
-    engines = []
-    for ci, cell in enumerate(cells):
-        e_ = P.make_engine(combo(cell, real), workload_hyper(cell), N, first_agent_id=sh.shard(rank, N), device=local_rank,
-                           store_kind=args.store)
-        e_.set_stream(group_streams[ci % n_groups].cuda_stream)
-        engines.append(e_)
-    pool = None
-    if n_groups > 1:   # the C ABI's train call returns when its launch is done: one host thread per stream keeps them all busy
-        from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(n_groups)
-    eng = engines[0]
-    table_bytes = sum(N * e_.S * e_.T * e_.A * real_size for e_ in engines)   # every env's rows are unpadded (Taxi: 24-byte f32 rows)
-
-    sums_dev = [torch.zeros((chunk, 4), dtype=torch.float64, device="cuda") for _ in cells]
-    rec_dtype_size = 16 if real == 0 else 32
-    state = {"k": 0}
-    acc = {"train_steps": 0, "eval_steps": 0, "kernel_ms": 0.0, "launches": 0, "trace_rows": 0, "alg_bytes": 0}
-
-    def run_cell(ci, k, c, host_out):
-        e_ = engines[ci]
-        if c == 0 and k > 0:
-            e_.agent_reset()                                    # src/bin/taxi.rs:200
-        if host_out is None:
-            return e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=sums_dev[ci])
-        return e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=host_out[0][ci], episodes_out=host_out[1][ci])
-
-    def step(host_out=None, count=True):
-        k = state["k"]
-        c = k % chunks_per_run
-        if pool is None:
-            results = None
-        else:                                                   # group g drives cells g, g + n_groups, ... in order on its stream
-            def run_group(g):
-                torch.cuda.set_device(local_rank)
-                return [(ci, run_cell(ci, k, c, host_out)) for ci in range(g, len(cells), n_groups)]
-            results = dict(x for grp in pool.map(run_group, range(n_groups)) for x in grp)
-        for ci, (cell, e_) in enumerate(zip(cells, engines)):
-            r = run_cell(ci, k, c, host_out) if results is None else results[ci]
-            if world > 1:                                       # the path's one collective: per-episode metrics to rank 0
-                if host_out is not None:
-                    sums_dev[ci].copy_(host_out[0][ci], non_blocking=True)
-                state["curves"] = sh.gather_episode_sums(sums_dev[ci])   # [world, chunk, 4] on rank 0
-            if count:
-                acc["train_steps"] += r["train_steps"]; acc["eval_steps"] += r["eval_steps"]
-                acc["kernel_ms"] += r["kernel_ms"]; acc["launches"] += 2 * r["kernel_launches"]   # each k_run is followed by one k_episode_sums
-                acc["trace_rows"] += r["trace_rows"]
-                acc["alg_bytes"] += algorithmic_bytes(cell, real_size, r["train_steps"], r["trace_rows"])
-        state["k"] = k + 1
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step(count=False)
-    # Timing rules: a run that saw a hardware / thermal slowdown is rejected and measured once more (sw_power_cap is
-    # kept and noted in `clocks.reasons`).  Every rank must take the same decision, so the flag is max-reduced.
-    remeasured = False
-    for attempt in range(2):
-        acc.update(train_steps=0, eval_steps=0, kernel_ms=0.0, launches=0, trace_rows=0, alg_bytes=0)
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall0 = time.perf_counter()
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step()
-        ev1.record(stream)
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-        clocks = sampler.stop()
-        ms = ev0.elapsed_time(ev1)
-        slowed = float(any(r in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown") for r in clocks.get("reasons", [])))
-        if world > 1:
-            flag = torch.tensor([slowed], dtype=torch.float64, device="cuda")
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-            slowed = float(flag.item())
-        if not slowed or attempt == 1:
-            break
-        remeasured = True
-    clocks["remeasured_after_slowdown"] = remeasured
-    dev = acc.copy()
-
-    # ---- e2e leg: same steps, host buffers, copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        host_sums = [torch.zeros((chunk, 4), dtype=torch.float64).pin_memory() for _ in cells]
-        host_eps = [torch.zeros((chunk, N, rec_dtype_size // 4), dtype=torch.int32).pin_memory() for _ in cells]
-        acc.update(train_steps=0, eval_steps=0, kernel_ms=0.0, launches=0, trace_rows=0, alg_bytes=0)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            step(host_out=(host_sums, host_eps))
-        e1.record(stream)
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
-        e2e = {"ms": e2e_ms, "train_steps": acc["train_steps"],
-               "d2h": len(cells) * (chunk * N * rec_dtype_size + chunk * 32 + 64), "h2d": 24 * len(cells)}
-
-    # ---- reduce over ranks: max time, sum of units
-    def allreduce(vals, op):
-        if world == 1:
-            return vals
-        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=op)
-        return t.tolist()
-    tmax = allreduce([ms, e2e["ms"] if e2e else 0.0, dev["kernel_ms"]], dist.ReduceOp.MAX if world > 1 else None)
-    tsum = allreduce([dev["train_steps"], dev["eval_steps"], e2e["train_steps"] if e2e else 0, dev["trace_rows"]],
-                     dist.ReduceOp.SUM if world > 1 else None)
-    if rank == 0:
-        ms_max, e2e_ms_max, kernel_ms_max = tmax
-        train_steps, eval_steps, e2e_steps, trace_rows = tsum
-        value = train_steps / (ms_max * 1e-3)
-        peak, peak_src = peaks()
-        # dominant kernel = k_run; per-launch duration measured live by the library (CUDA events on the engine's stream)
-        n_launch = max(1, dev["launches"] // 2)                   # k_run launches on this rank (each followed by one k_episode_sums)
-        alg_bytes = dev["alg_bytes"]
-        achieved = alg_bytes / (dev["kernel_ms"] * 1e-3) / 1e9 if dev["kernel_ms"] > 0 else 0.0
-        line = {
-            "metric": "agent-env steps/sec (updates incl.)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / max(1, args.steps), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.real, "data": "synthetic",
-            "config": {"workload": args.workload + ": " + w["desc"], "agents_per_gpu": N * len(cells), "agents_total": N * len(cells) * world, "cells": len(cells),
-                       "episodes_per_step": chunk, "n_episodes": n_ep, "eval_at": eval_at,
-                       "table_store": {1: "hbm", 2: "shared_memory_groups", 3: "hybrid_smem_q_l2_traces"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)],
-                       "eval_steps_executed_not_counted": eval_steps, "env_steps_per_s_incl_eval": (train_steps + eval_steps) / (ms_max * 1e-3),
-                       "l2": "inputs larger than L2: %.2f GB of per-agent tables per GPU vs 126 MB L2 (no flush needed)" % (table_bytes / 1e9),
-                       "parallelism": "agents sharded by global id, %d per GPU; one NCCL gather of [episodes,4] metrics per step" % N
-                                      + ("; the %d cells' engines spread over %d host threads / CUDA streams (their launches overlap, so "
-                                         "kernel_share_of_step counts concurrent kernels)" % (len(cells), n_groups) if n_groups > 1 else ""),
-                       "wall_s": t_wall},
-            "clocks": clocks,
-            "gpu_launches": int(dev["launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_run", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(args.workload, N, args.real) if len(cells) == 1 else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes / n_launch, "launch_ms": dev["kernel_ms"] / n_launch,
-                         "kernel_share_of_step": dev["kernel_ms"] / ms if ms > 0 else None},
-        }
-        if e2e:
-            line["e2e"] = {"value": e2e_steps / (e2e_ms_max * 1e-3), "unit": "agent-steps/s",
-                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "note": "C-ABI rlb_agent_train_range with pinned HOST buffers: per-agent episode records + per-episode sums copied "
-                                   "device->host every step; the path has no per-step host inputs besides the call's scalar arguments"}
-        if world == 1 and not args.no_cpu_baseline:
-            cpu_agents = 512 if len(cells) == 1 else 4   # ~10 s of single-thread CPU work
-            ts, dt = 0, 0.0
-            for cell in cells:
-                ts_, dt_, _ = cpu_sample(cell, real, cpu_agents, 1, 0, n_ep)
-                ts += ts_; dt += dt_
-            line["cpu_baseline"] = {"value": ts / dt, "unit": "agent-steps/s", "cores": 1, "kind": "port",
-                                    "sample": "%d agents%s x one full %d-episode run (eval_at %d), C++ oracle single thread, %.1f s"
-                                              % (cpu_agents, " per cell" if len(cells) > 1 else "", n_ep, eval_at, dt)}
+    job = Job()
+    cpu_agents = 0 if args.no_cpu_baseline else (512 if "cells" not in w else 4)   # ~10 s of single-thread CPU work
+    line = measure(job, args, args.workload, w, real, args.steps, args.warmup, not args.no_e2e, cpu_agents, args.cell_streams)
+    sub_records = {}
+    saved_apg = args.agents_per_gpu
+    for sname in subs:
+        args.agents_per_gpu = 0
+        base, _, suffix = sname.partition("_")
+        sw = dict(W.WORKLOADS[base])
+        sreal = 1 if suffix == "f64" else 0
+        # CPU samples of the sub-records are sized for a few seconds each (C3 executes ~6x its training steps in evaluate)
+        scpu = 0 if args.no_cpu_baseline else {"c4": 512, "c3": 64, "c2": 256, "c1": 512}.get(base, 0)
+        r = measure(job, args, base, sw, sreal, args.sub_steps, max(3, args.sub_warmup), not args.no_e2e, scpu, args.cell_streams)
+        if r is not None:
+            sub_records[sname] = r
+    args.agents_per_gpu = saved_apg
+    if job.rank == 0:
+        if sub_records:
+            line["workloads"] = sub_records
         print(json.dumps(line), flush=True)
-    if pool is not None:
-        pool.shutdown()
-    for e_ in engines:
-        e_.close()
-    if world > 1:
-        dist.destroy_process_group()
+    job.close()
 
 
 if __name__ == "__main__":

@@ -202,7 +202,7 @@ size_t store_bytes(rlb_engine* e, int store) {
 rlb_status pick_store(rlb_engine* e) {
     const size_t per_block_max = 227 * 1024, per_sm = 228 * 1024;
     const size_t b_group = store_bytes(e, STORE_SMEM), b_hybrid = store_bytes(e, STORE_HYBRID);
-    const bool fits_group = b_group > 0 && b_group <= per_block_max;
+    const bool fits_group = b_group > 0 && b_group <= per_block_max && e->S <= 256;      // GroupStore keeps visited states in 8 bits
     const bool fits_hybrid = b_hybrid > 0 && b_hybrid <= per_block_max && e->S <= 64;   // DevParams::row_lut holds 64 states
     int want = e->cfg.store_kind;
     if (e->cfg.planning_steps) {

@@ -116,3 +116,29 @@ def test_mirror_has_the_reference_names(rlb):
         agent.train(env, 10, 0)                               # agent.rs:107 `episode % eval_at` with eval_at == 0 panics
     for m in ("set_future_q_value_func", "set_action_selector", "get_action", "update", "reset", "train", "evaluate"):
         assert callable(getattr(agent, m))
+
+
+def test_comm_entry_points_without_a_gpu(rlb):
+    """rlb_comm_*: NCCL is resolved at run time (dlopen); the unique id needs no device, a communicator does — and says so."""
+    uid = rlb.abi.Comm.unique_id()
+    assert len(uid) == rlb.abi.COMM_ID_BYTES and uid != bytes(128)
+    if rlb.abi.lib.rlb_device_count() == 0:
+        with pytest.raises(rlb.RlbError) as ei:
+            rlb.abi.Comm.init_rank(uid, 1, 0, 0)
+        assert ei.value.status in (rlb.abi.ERR_CUDA, rlb.abi.ERR_NCCL)
+        with pytest.raises(rlb.RlbError):
+            rlb.abi.Comm.init_all([0])
+    with pytest.raises(rlb.RlbError) as ei:
+        rlb.abi.Comm.init_rank(uid, 2, 5, 0)          # rank out of range
+    assert ei.value.status == rlb.abi.ERR_INVALID_ARG
+    assert rlb.abi.lib.rlb_comm_rank(None) == -1 and rlb.abi.lib.rlb_comm_world_size(None) == 0
+
+
+def test_shard_sizes(rlb):
+    import importlib
+    sh = importlib.import_module("rl-rust_b200.sharding")
+    for total, n in ((1 << 24, 8), (1 << 24, 2), (10, 3), (7, 7)):
+        parts = sh.shard_sizes(total, n)
+        assert sum(c for _, c in parts) == total and parts[0][0] == 0
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(n - 1))
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1

@@ -8,6 +8,37 @@ import pytest
 from oracle import oracle_py as O
 
 
+def sequential_moving_average(window, v):
+    """utils.rs:78-93 restated with plain Python floats: left-to-right sums, the short last slice divided by the window."""
+    out, aux = [], 0
+    while window > 0 and aux < len(v):
+        end = aux + window if aux + window < len(v) else len(v)
+        acc = 0.0
+        for x in v[aux:end]:
+            acc += float(x)
+        out.append(acc / float(window))
+        aux = end
+    return out
+
+
+def P_bits_equal(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and bool(np.all((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))))
+
+
+def LEGENDS_I(res, i):
+    return "%s (%s)" % (res["legends"][i], res.get("train_errors_kind"))
+
+
+def test_moving_average_is_sequential():
+    drv = importlib.import_module("rl-rust_b200.driver")
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(10007) * 10.0 ** rng.integers(-8, 8, 10007)
+    for w in (1, 7, 100, 4096, 10007, 20000):
+        assert P_bits_equal(drv.moving_average(w, v), sequential_moving_average(w, v))
+    assert drv.moving_average(0, v) == []      # the reference would loop forever on a zero window (utils.rs:81-90)
+
+
 def test_moving_average_quirk():
     drv = importlib.import_module("rl-rust_b200.driver")
     v = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0]
@@ -19,7 +50,8 @@ def test_moving_average_quirk():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env_name,env_kind", [("taxi", O.ENV_TAXI), ("frozen_lake", O.ENV_FROZEN_LAKE), ("blackjack", O.ENV_BLACKJACK)])
+@pytest.mark.parametrize("env_name,env_kind", [("taxi", O.ENV_TAXI), ("frozen_lake", O.ENV_FROZEN_LAKE), ("blackjack", O.ENV_BLACKJACK),
+                                               ("cliffwalking", O.ENV_CLIFF_WALKING)])
 def test_twelve_run_matrix_matches_oracle(env_name, env_kind):
     """bin/taxi.rs:158-203 with n_agents = 1: every curve of every one of the 12 runs equals the oracle's, i.e. the two
     agent objects really share one env and one stream."""
@@ -41,6 +73,10 @@ def test_twelve_run_matrix_matches_oracle(env_name, env_kind):
                 assert res["train_steps"][i] == int(ln.sum())
                 assert res["train_rewards"][i] == drv.moving_average(window, ret)
                 assert res["train_episodes_length"][i] == drv.moving_average(window, ln.astype(np.float64))
+                # "Training Error": windows of training_error.len() / moving_average_window raw per-step TDs (bin/taxi.rs:170-174)
+                te = s.training_error()
+                assert len(te) == int(ln.sum())
+                assert P_bits_equal(res["train_errors"][i], sequential_moving_average(len(te) // 10, te)), LEGENDS_I(res, i)
                 if env_name == "blackjack":
                     eret, _ = s.evaluate(300)
                     assert res["blackjack_rates"][i] == (float((eret == 1).sum()) / 300, float((eret == -1).sum()) / 300,
@@ -72,6 +108,8 @@ def test_cliffwalking_model_bin_matches_oracle():
         assert res["train_steps"][i] == int(ln.sum())
         assert res["train_rewards"][i] == drv.moving_average(window, ret)
         assert res["train_episodes_length"][i] == drv.moving_average(window, ln.astype(np.float64))
+        te = s.training_error()
+        assert P_bits_equal(res["train_errors"][i], sequential_moving_average(len(te) // 10, te))
         eret, eln = s.evaluate(n)
         assert res["test_rewards"][i] == drv.moving_average(window, eret)
         assert res["test_episodes_length"][i] == drv.moving_average(window, eln.astype(np.float64))
@@ -79,3 +117,19 @@ def test_cliffwalking_model_bin_matches_oracle():
     assert res["final_rng_n"][0] == s.export()[2].rng_n
     assert sum(res["train_episodes_length"][1]) < sum(res["train_episodes_length"][0])   # planning pays
     s.close()
+
+
+@pytest.mark.gpu
+def test_driver_multi_gpu_matches_single_gpu(rlb):
+    """`--gpus 2`: the agents sharded over two GPUs (one engine each, asynchronous train calls, NCCL gather of the
+    per-episode sums) give the curves of the same agents on one GPU — per-agent results do not depend on the sharding."""
+    if rlb.abi.lib.rlb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    drv = importlib.import_module("rl-rust_b200.driver")
+    kw = dict(n_agents=64, seed=0xBEEF, real="f64", tally_games=0, verbose=False, n_episodes=20, moving_average_window=10)
+    one = drv.run_experiment("taxi", gpus=1, **kw)
+    two = drv.run_experiment("taxi", gpus=2, **kw)
+    for k in ("train_rewards", "train_episodes_length", "test_rewards", "test_episodes_length", "train_steps"):
+        assert one[k] == two[k], k
+    for a, b in zip(one["train_errors"], two["train_errors"]):
+        assert P_bits_equal(a, b)
