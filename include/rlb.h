@@ -358,6 +358,12 @@ rlb_status rlb_comm_allreduce_sum(rlb_comm* c, double* values, uint64_t count, v
 rlb_status rlb_comm_group_begin(void);
 rlb_status rlb_comm_group_end(void);
 
+/* ---- self test ---------------------------------------------------------------------------------------------------
+ * The UCB bonus sqrt(ln t / n) (upper_confidence_bound.rs:33-37) is computed with hand-scheduled copies of the
+ * compiler's own division / square-root sequences; this compares them with the compiler's, bit for bit, on `samples`
+ * pseudo-random (t in [2, t_max], n in [1, n_max]) pairs and reports the number of differing results (expected: 0). */
+rlb_status rlb_selftest_ucb_math(int32_t device, uint64_t samples, uint64_t t_max, uint64_t n_max, uint64_t seed, uint64_t* mismatches_out);
+
 /* ---- RNG injection contract, host-callable (no device needed) -------------------------------
  * Replaces rand::thread_rng() at blackjack.rs:54,76; taxi.rs:136-137; frozen_lake.rs:107-108,126;
  * uniform_epsilon_greed.rs:53,62; random_model.rs:30.  Stream of agent g: 32-bit words

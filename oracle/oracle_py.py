@@ -132,6 +132,8 @@ ENV_DIMS = {ENV_BLACKJACK: (1456, 2), ENV_CLIFF_WALKING: (48, 4), ENV_TAXI: (500
 
 def env_dims(cfg):
     if cfg.env_kind == ENV_FROZEN_LAKE:
+        if cfg.map_id == 2:
+            return (cfg.map_rows * cfg.map_cols, 4)
         return (16 if cfg.map_id == 0 else 64, 4)
     return ENV_DIMS[cfg.env_kind]
 

@@ -73,6 +73,7 @@ EXPORTS = [
     "rlb_agent_train_range_async", "rlb_agent_train_wait", "rlb_agent_step",
     "rlb_comm_unique_id", "rlb_comm_init_rank", "rlb_comm_init_all", "rlb_comm_destroy", "rlb_comm_rank", "rlb_comm_world_size",
     "rlb_comm_gather_episode_sums", "rlb_comm_allreduce_sum", "rlb_comm_group_begin", "rlb_comm_group_end",
+    "rlb_selftest_ucb_math",
 ]
 
 
@@ -143,6 +144,7 @@ def _load():
     L.rlb_comm_allreduce_sum.argtypes = [vp, vp, u64, vp]
     L.rlb_comm_group_begin.argtypes = []
     L.rlb_comm_group_end.argtypes = []
+    L.rlb_selftest_ucb_math.argtypes = [i32, u64, u64, u64, u64, P(u64)]
     L.rlb_policy_predict.argtypes = [vp, vp, vp]
     L.rlb_policy_get_values.argtypes = [vp, vp, vp]
     L.rlb_policy_update.argtypes = [vp, vp, vp, vp, vp]

@@ -79,6 +79,7 @@ struct rlb_engine {
     // rlb_agent_step: curr_obs / curr_action of every agent
     uint32_t* d_cur_obs = nullptr;
     uint32_t* d_cur_action = nullptr;
+    void* h_step_stage = nullptr; size_t step_stage_cap = 0;   // rlb_agent_step: mapped pinned block for host outputs
     double* d_log_table = nullptr;     // ln(t) for t < RLB_LOG_TABLE_N (UCB), filled on the device by portable_log
     // Calls whose work is enqueued but not yet waited for (rlb_agent_train_range_async): at most two, so that the
     // kernels of call i + 1 are in the queue before the host blocks on the copies of call i.
@@ -314,6 +315,12 @@ rlb_status install_selector(rlb_engine* e, int kind) {
             CK(cudaMalloc(&e->d_counts, e->counts_bytes));
         }
         CK(cudaMemsetAsync(e->d_counts, 0, e->counts_bytes, e->stream));
+        if (!e->d_log_table) {   // ln(t) table of the UCB bonus
+            CK(cudaMalloc(&e->d_log_table, (size_t)RLB_LOG_TABLE_N * sizeof(double)));
+            k_fill_log_table<<<(RLB_LOG_TABLE_N + 255) / 256, 256, 0, e->stream>>>(e->d_log_table, RLB_LOG_TABLE_N);
+            CK(cudaGetLastError());
+            e->dp.log_table = e->d_log_table; e->dp.log_table_n = RLB_LOG_TABLE_N;
+        }
     }
     e->dp.counts = e->d_counts;
     return RLB_OK;
@@ -464,7 +471,7 @@ rlb_status finish_pending(rlb_engine* e) {
     } while (0)
 
 rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, uint64_t eval_at, rlb_train_out* out,
-                         void* eval_episodes_out, double* eval_sums_out, uint64_t* eval_steps_out) {
+                         void* eval_episodes_out, double* eval_sums_out, uint64_t* eval_steps_out, bool async_call = false) {
     const uint64_t N = e->cfg.n_agents;
     const size_t rec = episode_rec_size(e);
     const uint64_t total = end - begin;
@@ -478,7 +485,10 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
     const bool pipelined = rec_host && !is_device_ptr(rec_host) && total >= 8;
     if (want_records) {
         chunk = std::min<uint64_t>(chunk, chunk_episodes(e, total));
-        if (pipelined) chunk = std::max<uint64_t>(1, std::min<uint64_t>((chunk + 1) / 2, (total + 3) / 4));
+        // A blocking call hides its record copy behind its own kernels: at least four launches over the two halves.  An
+        // asynchronous call hides it behind the NEXT call's kernel, so it stays ONE launch when its records fit a half
+        // (each extra launch costs its tail: the last CTAs of a 32 768-CTA grid run on a mostly idle GPU).
+        if (pipelined) chunk = std::max<uint64_t>(1, std::min<uint64_t>((chunk + 1) / 2, async_call ? total : (total + 3) / 4));
     }
     // A call may only overlap the one before it when both stream records through the same two scratch halves.
     if (!e->pending.empty() && !(pipelined && e->pending.back().pipelined && chunk == e->last_pipeline_chunk && total <= e->sums_cap / (4 * sizeof(double)))) {
@@ -659,6 +669,7 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     p.td_steps = nullptr; p.td_cap = 0; p.td_count = nullptr;
     p.cur_obs = nullptr; p.cur_action = nullptr;
     p.fl_start = e->tables.fl_start;
+    p.log_table = nullptr; p.log_table_n = 0;
     p.model_ent = nullptr; p.model_bits = nullptr; p.model_len = nullptr; p.planning_steps = 0; p.mcap = 0; p.mwords = 0;
 
     CKE(fill_q_default(e));
@@ -688,6 +699,7 @@ void rlb_engine_destroy(rlb_engine* e) {
     if (e->d_cur_obs) cudaFree(e->d_cur_obs);
     if (e->d_cur_action) cudaFree(e->d_cur_action);
     if (e->d_log_table) cudaFree(e->d_log_table);
+    if (e->h_step_stage) cudaFreeHost(e->h_step_stage);
     void* bufs[] = {e->d_q, e->d_counts, e->d_etr, e->d_etr_il, e->d_vis, e->d_nvis, e->d_rng_n, e->d_eps, e->d_ucb_t, e->d_flag, e->d_env,
                     e->d_trans, e->d_thr, e->d_thr_state, e->d_totals, e->d_flagword, e->d_episodes, e->d_sums,
                     e->d_model_ent, e->d_model_bits, e->d_model_len};
@@ -820,25 +832,32 @@ rlb_status rlb_agent_step(rlb_engine* e, uint8_t* kind_out, uint32_t* obs_out, u
         CK(cudaMemsetAsync(e->d_cur_action, 0, N * 4, e->stream));
         e->dp.cur_obs = e->d_cur_obs; e->dp.cur_action = e->d_cur_action;
     }
+    // Outputs for HOST buffers are written by the kernel straight into one block of mapped pinned memory (the device
+    // sees it through unified addressing) and copied out by the CPU after the single wait: launch + wait is the whole
+    // latency of a transition, with no per-array cudaMemcpy.  DEVICE buffers are written in place.
+    const size_t sizes[6] = {(size_t)N * 8, (size_t)N * e->real_size, (size_t)N * 4, (size_t)N * 4, (size_t)N, (size_t)N};   // reward, td, obs, action, kind, terminated
+    void* const user[6] = {reward_out, td_out, obs_out, action_out, kind_out, terminated_out};
+    size_t need = 0;
+    for (int k = 0; k < 6; ++k) if (user[k] && !is_device_ptr(user[k])) need += (sizes[k] + 15) & ~(size_t)15;
+    if (need > e->step_stage_cap) {
+        if (e->h_step_stage) cudaFreeHost(e->h_step_stage);
+        e->h_step_stage = nullptr; e->step_stage_cap = 0;
+        CK(cudaHostAlloc(&e->h_step_stage, need, cudaHostAllocMapped));
+        e->step_stage_cap = need;
+    }
+    void* dev[6];
+    size_t off = 0;
+    for (int k = 0; k < 6; ++k) {
+        if (!user[k]) dev[k] = nullptr;
+        else if (is_device_ptr(user[k])) dev[k] = user[k];
+        else { dev[k] = (char*)e->h_step_stage + off; off += (sizes[k] + 15) & ~(size_t)15; }
+    }
     StepArgs a;
-    void *d_kind, *d_obs, *d_act, *d_rew, *d_term, *d_td;
-    CK(stage_out(e, 0, kind_out, N, &d_kind));
-    CK(stage_out(e, 1, obs_out, N * 4, &d_obs));
-    CK(stage_out(e, 2, action_out, N * 4, &d_act));
-    CK(stage_out(e, 3, reward_out, N * 8, &d_rew));
-    CK(stage_out(e, 4, terminated_out, N, &d_term));
-    CK(stage_out(e, 5, td_out, N * e->real_size, &d_td));
-    a.kind_out = (uint8_t*)d_kind; a.u32_out = (uint32_t*)d_obs; a.u32_out2 = (uint32_t*)d_act; a.reward_out = (double*)d_rew;
-    a.term_out = (uint8_t*)d_term; a.real_out = d_td;
+    a.reward_out = (double*)dev[0]; a.real_out = dev[1]; a.u32_out = (uint32_t*)dev[2]; a.u32_out2 = (uint32_t*)dev[3];
+    a.kind_out = (uint8_t*)dev[4]; a.term_out = (uint8_t*)dev[5];
     CK(dispatch_step(e, OP_AGENT_STEP, a));
-    // one wait for the whole call: the copies of the (small) outputs ride the stream
-    CK(copy_async(e, kind_out, d_kind, kind_out == d_kind ? 0 : N));
-    CK(copy_async(e, obs_out, d_obs, obs_out == d_obs ? 0 : N * 4));
-    CK(copy_async(e, action_out, d_act, action_out == d_act ? 0 : N * 4));
-    CK(copy_async(e, reward_out, d_rew, reward_out == d_rew ? 0 : N * 8));
-    CK(copy_async(e, terminated_out, d_term, terminated_out == d_term ? 0 : N));
-    CK(copy_async(e, td_out, d_td, td_out == d_td ? 0 : N * e->real_size));
     CK(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < 6; ++k) if (user[k] && dev[k] != user[k]) std::memcpy(user[k], dev[k], sizes[k]);
     return RLB_OK;
 }
 
@@ -1019,7 +1038,7 @@ rlb_status rlb_agent_train_range_async(rlb_engine* e, uint64_t ep_begin, uint64_
     rlb_status st = check_train_args(e, ep_begin, ep_end, eval_at);
     if (st != RLB_OK) return st;
     CK(cudaSetDevice(e->cfg.device));
-    st = enqueue_range(e, 0, ep_begin, ep_end, eval_at, out, nullptr, nullptr, nullptr);
+    st = enqueue_range(e, 0, ep_begin, ep_end, eval_at, out, nullptr, nullptr, nullptr, true);
     if (st != RLB_OK) { finish_pending(e); return st; }
     // the new call's kernels are in the queue: now the host may block on the call before it
     while (e->pending.size() > 1) {
@@ -1230,6 +1249,22 @@ rlb_status rlb_set_agent_states(rlb_engine* e, const rlb_agent_state* states) {
     CK(cudaMemcpyAsync(e->d_rng_n, n.data(), N * 8, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->d_flag, flag.data(), N, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return RLB_OK;
+}
+
+// ------------------------------------------------------------------------------- self tests
+rlb_status rlb_selftest_ucb_math(int32_t device, uint64_t samples, uint64_t t_max, uint64_t n_max, uint64_t seed, uint64_t* mismatches_out) {
+    if (!mismatches_out || t_max < 2 || n_max < 1 || n_max > 0xffffffffull) { set_error("bad arguments"); return RLB_ERR_INVALID_ARG; }
+    CK(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 8));
+    CK(cudaMemset(d, 0, 8));
+    k_selftest_ucb_math<<<148 * 8, 256>>>(samples, t_max, n_max, seed, d);
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches_out = h;
     return RLB_OK;
 }
 

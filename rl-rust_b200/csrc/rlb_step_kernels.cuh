@@ -332,6 +332,31 @@ static __global__ void k_flag_flip(uint8_t* flag, uint64_t n) {
     if (i < n) flag[i] = flag[i] ? 0 : 1;
 }
 
+// ln(t) for t < n, by the engine's own portable_log (DevParams::log_table)
+static __global__ void k_fill_log_table(double* tab, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tab[i] = i == 0u ? 0.0 : portable_log((double)i);   // entry 0 is never read: t starts at 1
+}
+
+// Test hook (rlb_selftest_ucb_math): div_fast / sqrt_fast against the compiler's own division and square root over the
+// UCB domain — ln(t) for t in [2, t_max], n in [1, n_max] — on a grid-stride sample; counts mismatching bit patterns.
+static __global__ void k_selftest_ucb_math(uint64_t samples, uint64_t t_max, uint64_t n_max, uint64_t seed, unsigned long long* mismatches) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (; i < samples; i += stride) {
+        uint64_t x = (i + seed) * 0x9E3779B97F4A7C15ull;   // splitmix-style scramble of the sample index
+        x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+        const uint64_t t = 2u + (x % (t_max - 1u));
+        const uint64_t n = 1u + ((x >> 32) % n_max);
+        const double a = portable_log((double)(long long)t), b = (double)(long long)n;
+        const double q_ref = a / b, q = div_fast(a, b);
+        const double r_ref = sqrt(q_ref), r = sqrt_fast(q);
+        bad += (__double_as_longlong(q_ref) != __double_as_longlong(q)) + (__double_as_longlong(r_ref) != __double_as_longlong(r));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 template <typename V>
 __global__ void k_fill(V* ptr, uint64_t n, V value) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
