@@ -156,6 +156,18 @@ inline u64 fxhash_blackjack(u8 p_score, u8 d_score, bool p_ace) {
 // (x = 2^k (1+f), s = f/(2+f), log(1+f) = 2s + s*R(s^2), 14-term minimax split in two
 // chains), evaluated with plain round-to-nearest +,-,*,/ and no FMA.  < 1 ulp.  Only
 // finite x >= 1 is needed (x = t as f64, t >= 1).
+inline double portable_log(double x);
+// `(self.t as f64).ln()` (upper_confidence_bound.rs:36,56).  Rust's f64::ln is the platform libm's log; the engine and
+// the oracle share ONE portable routine instead so that host and device agree bit for bit.  Building
+// with -DORACLE_LIBM_LOG swaps in this machine's libm (glibc) — used only by tools/log_sensitivity.py to measure how
+// far the choice of log reaches into UCB trajectories.
+inline double ucb_ln(double x) {
+#ifdef ORACLE_LIBM_LOG
+    return std::log(x);
+#else
+    return portable_log(x);
+#endif
+}
 inline double portable_log(double x) {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
     const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
@@ -714,7 +726,7 @@ struct UpperConfidenceBound : ActionSelection<A, Real> {
         double ucbs[A];
         for (int i = 0; i < A; ++i)
             ucbs[i] = (double)values[i] +
-                      confidence_level * std::sqrt(portable_log((double)t) / ((double)obs_actions[i] + DBL_MIN));
+                      confidence_level * std::sqrt(ucb_ln((double)t) / ((double)obs_actions[i] + DBL_MIN));
         size_t action = argmax<double>(ucbs, A);
         obs_actions[action] += 1;
         t += 1;
@@ -728,7 +740,7 @@ struct UpperConfidenceBound : ActionSelection<A, Real> {
         double sum = 0.0;
         for (int i = 0; i < A; ++i) {
             ucbs[i] = (double)values[i] +
-                      confidence_level * std::sqrt(portable_log((double)t) / ((double)obs_actions[i] + DBL_MIN));
+                      confidence_level * std::sqrt(ucb_ln((double)t) / ((double)obs_actions[i] + DBL_MIN));
             sum += ucbs[i];
         }
         Row out;

@@ -24,7 +24,7 @@ __global__ void k_env_construct(const DevParams p) {
     es.pos = 0; es.curr_step = 0; es.ready = 0;
     es.p_sum = es.d_sum = es.d_first = 0; es.p_ace = es.d_ace = 0; es.pad[0] = es.pad[1] = 0;
     if constexpr (ENV == RLB_ENV_BLACKJACK) {
-        Rng rng;
+        EnvRng<ENV> rng;
         rng.init(p, p.first_agent + i, p.rng_n[i]);
         EnvRegs<RLB_ENV_BLACKJACK> env;
         env.deal(rng, p);
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128) k_env_reset(const DevParams p, uint32_t* 
     __syncthreads();
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_agents) return;
-    Rng rng;
+    EnvRng<ENV> rng;
     rng.init(p, p.first_agent + i, p.rng_n[i]);
     EnvState es = p.env[i];
     EnvRegs<ENV> env;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128) k_env_step(const DevParams p, const uint3
     }
     if (not_ready_out) not_ready_out[i] = 0;
     if (actions[i] >= (uint32_t)EnvDims<ENV>::A) { atomicOr(any_not_ready, FLAG_BAD_ARG); return; }
-    Rng rng;
+    EnvRng<ENV> rng;
     rng.init(p, p.first_agent + i, p.rng_n[i]);
     EnvRegs<ENV> env;
     env.from_state(es);
