@@ -267,7 +267,11 @@ def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_
     table_bytes = sum(N * e_.S * e_.T * e_.A * real_size for e_ in engines)   # every env's rows are unpadded (Taxi: 24-byte f32 rows)
 
     sums_dev = [torch.zeros((chunk, 4), dtype=torch.float64, device="cuda") for _ in cells]
-    gathered = [torch.zeros((world, chunk, 4), dtype=torch.float64, device="cuda") for _ in cells] if (world > 1 and rank == 0) else None
+    # rank 0 receives the gathered curves; two buffers take turns so that the e2e leg's device->host copy of step k (on a
+    # side stream: a device->host copy on the main stream would queue behind the record copy and stall the next kernel)
+    # is never overwritten by the gather of step k + 1
+    gathered = [[torch.zeros((world, chunk, 4), dtype=torch.float64, device="cuda") for _ in range(2)] for _ in cells] if (world > 1 and rank == 0) else None
+    side = torch.cuda.Stream() if (world > 1 and rank == 0) else None
     rec_size = 16 if real == 0 else 32
     state = {"k": 0}
     acc = {}
@@ -296,10 +300,12 @@ def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_
             e_.train((c + 1) * chunk, eval_at, ep_begin=c * chunk, sums_out=sums_target, episodes_out=rec_target, wait=False)
             if world > 1:                                       # the path's one collective: per-episode metrics to rank 0 (rlb_comm, NCCL)
                 s_ = group_streams[ci % n_groups]
-                job.sh.gather_episode_sums(sums_dev[ci], comm=job.comm, out=gathered[ci] if rank == 0 else None, stream=s_.cuda_stream)
+                g_ = gathered[ci][k & 1] if rank == 0 else None
+                job.sh.gather_episode_sums(sums_dev[ci], comm=job.comm, out=g_, stream=s_.cuda_stream)
                 if host is not None and rank == 0:              # e2e: the gathered curves land in rank 0's host memory
-                    with torch.cuda.stream(s_):
-                        host[2][ci].copy_(gathered[ci], non_blocking=True)
+                    side.wait_stream(s_)
+                    with torch.cuda.stream(side):
+                        host[2][ci].copy_(g_, non_blocking=True)
         if wait:
             drain(count)
         state["k"] = k + 1
@@ -360,6 +366,8 @@ def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_
         for _ in range(steps):
             step(host=(host_sums, host_recs, host_gath), wait=not double_buf)
         drain(count=True)                                       # the last call's records are on the host when this returns
+        if side is not None:
+            stream.wait_stream(side)
         for s_ in group_streams[1:] if n_groups > 1 else []:
             stream.wait_stream(s_)
         e1.record(stream)

@@ -13,7 +13,11 @@
 // Blackjack observation id restates fxhash 0.2.1 — both un-vendored dependencies
 // (Cargo.toml:16,19).  What pins this oracle is (i) published KATs (Philox / Random123),
 // (ii) the [derived] constants of SURVEY.md §8.2, (iii) an independent pure-Python
-// restatement (`oracle/pyref.py`) cross-checked in tests/.
+// restatement (`oracle/pyref.py`) cross-checked in tests/, (iv) NVIDIA's own Philox (cuRAND
+// device API) producing the same word stream (tests/test_gpu_curand.py).  The reference-side
+// half of a real pin — the Philox `RngCore` for the crate, the patch of its nine
+// thread_rng() call sites, a dump binary and the test that compares — is in oracle/rust_ref/
+// (source only: it needs `cargo`); tests/test_rust_ref.py runs when oracle/_ref/ is built.
 //
 // Arithmetic contract (compile with -ffp-contract=off; x86-64 SSE2, no x87):
 //   Real = double  -> reference-faithful mode (the reference computes in f64 everywhere).

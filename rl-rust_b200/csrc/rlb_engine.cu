@@ -62,7 +62,8 @@ struct rlb_engine {
     uint2* d_model_ent = nullptr;       // Dyna model (only while an InternalModelAgent wraps the agent)
     uint32_t* d_model_bits = nullptr;
     uint32_t* d_model_len = nullptr;
-    unsigned long long* d_totals = nullptr;   // [8]: train steps, eval steps, eval episodes, (double) eval return, trace rows
+    unsigned long long* d_totals = nullptr;   // [3][8] (one block per call in flight): train steps, eval steps, eval episodes, (i64) eval return, trace rows
+    uint64_t call_counter = 0;                // picks the totals block and the sums region of a call
     uint32_t* d_flagword = nullptr;
     // scratch
     void* d_episodes = nullptr; size_t episodes_cap = 0;
@@ -491,15 +492,23 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
         if (pipelined) chunk = std::max<uint64_t>(1, std::min<uint64_t>((chunk + 1) / 2, async_call ? total : (total + 3) / 4));
     }
     // A call may only overlap the one before it when both stream records through the same two scratch halves.
-    if (!e->pending.empty() && !(pipelined && e->pending.back().pipelined && chunk == e->last_pipeline_chunk && total <= e->sums_cap / (4 * sizeof(double)))) {
+    if (!e->pending.empty() && !(pipelined && e->pending.back().pipelined && chunk == e->last_pipeline_chunk && 3 * total <= e->sums_cap / (4 * sizeof(double)))) {
         rlb_status st = finish_pending(e);
         if (st != RLB_OK) return st;
     }
+    // A call in flight owns one of three blocks of totals and of per-episode sums (at most two calls are pending while
+    // a third is being enqueued), so that nothing of call i + 1 on the main stream has to wait for the small
+    // device->host copies of call i: those ride the COPY stream behind call i's records.  (They used to sit on the main
+    // stream, where the copy engine served them in issue order BEHIND the 1.7–3.4 GB record copy — and the next call's
+    // kernel behind them: the whole record copy was serialised after all, profiles/r02e_e2e_probe_*.json.)
+    const uint64_t slot = e->call_counter++ % 3;
     if (want_records) {
-        rlb_status st = ensure_episode_scratch(e, pipelined ? 2 * chunk : chunk, total);
+        rlb_status st = ensure_episode_scratch(e, pipelined ? 2 * chunk : chunk, 3 * total);
         if (st != RLB_OK) return st;
         if (pipelined) { st = ensure_copy_pipeline(e); if (st != RLB_OK) return st; e->last_pipeline_chunk = chunk; }
     }
+    unsigned long long* const d_totals = e->d_totals + 8 * slot;
+    double* const d_sums_call = e->d_sums + (want_records ? slot * total * 4 : 0);
     rlb_engine::Pending pd;
     pd.mode = mode; pd.out = out; pd.eval_steps_out = eval_steps_out; pd.pipelined = pipelined;
     if (e->totals_pool.empty()) {
@@ -523,7 +532,7 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
         else { CK(cudaMalloc(&pd.d_td_count, N * sizeof(uint64_t))); pd.own_td_count = true; }
         CK(cudaMemsetAsync(pd.d_td_count, 0, N * sizeof(uint64_t), e->stream));
     }
-    CK(cudaMemsetAsync(e->d_totals, 0, 8 * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(d_totals, 0, 8 * sizeof(unsigned long long), e->stream));
     double* const sums_dst = mode == 0 ? (out ? out->episode_sums : nullptr) : eval_sums_out;
     void* const rec_dst = mode == 0 ? (out ? out->episodes : nullptr) : eval_episodes_out;
     for (uint64_t c0 = begin; c0 < end; c0 += chunk) {
@@ -536,6 +545,7 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
         DevParams p = e->dp;
         p.mode = mode;
         p.eval_at = eval_at;
+        p.totals = d_totals;
         if (mode == 0) { p.ep0 = c0; p.ep1 = c1; p.n_eval = 0; }
         else { p.ep0 = p.ep1 = 0; p.n_eval = c1 - c0; }
         p.episodes = want_records ? scratch : nullptr;
@@ -549,7 +559,7 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
         CK(cudaEventRecord(ev1, e->stream));
         const uint64_t n_ep = c1 - c0;
         if (sums_dst) {   // reads the records on the main stream, before that scratch is written again
-            rlb_status st = reduce_episodes(e, n_ep, scratch, e->d_sums + (c0 - begin) * 4);
+            rlb_status st = reduce_episodes(e, n_ep, scratch, d_sums_call + (c0 - begin) * 4);
             if (st != RLB_OK) return st;
         }
         if (pipelined) {
@@ -561,15 +571,23 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
             CK(copy_async(e, (char*)rec_dst + (c0 - begin) * N * rec, scratch, n_ep * N * rec));
         }
     }
-    if (sums_dst && total) CK(copy_async(e, sums_dst, e->d_sums, total * 4 * sizeof(double)));
-    CK(cudaMemcpyAsync(pd.h_totals, e->d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     pd.done = take_event(e);
     if (!pd.done) { set_error("cudaEventCreate failed"); return RLB_ERR_CUDA; }
-    CK(cudaEventRecord(pd.done, e->stream));
     if (pipelined) {
+        // kernels and reductions are in the main stream's queue; every device->host copy of this call goes to the copy stream
+        const bool sums_on_device = sums_dst && is_device_ptr(sums_dst);   // e.g. about to be gathered on the caller's stream: stays in stream order
+        if (sums_on_device && total) CK(cudaMemcpyAsync(sums_dst, d_sums_call, total * 4 * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaEventRecord(pd.done, e->stream));
+        CK(cudaStreamWaitEvent(e->copy_stream, pd.done, 0));
+        if (sums_dst && !sums_on_device && total) CK(cudaMemcpyAsync(sums_dst, d_sums_call, total * 4 * sizeof(double), cudaMemcpyDeviceToHost, e->copy_stream));
+        CK(cudaMemcpyAsync(pd.h_totals, d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->copy_stream));
         pd.copies_done = take_event(e);
         if (!pd.copies_done) { set_error("cudaEventCreate failed"); return RLB_ERR_CUDA; }
         CK(cudaEventRecord(pd.copies_done, e->copy_stream));
+    } else {
+        if (sums_dst && total) CK(copy_async(e, sums_dst, d_sums_call, total * 4 * sizeof(double)));
+        CK(cudaMemcpyAsync(pd.h_totals, d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaEventRecord(pd.done, e->stream));
     }
     e->pending.push_back(std::move(pd));
     return RLB_OK;
@@ -633,7 +651,7 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     CKE(cudaMalloc(&e->d_ucb_t, N * sizeof(uint64_t)));
     CKE(cudaMalloc(&e->d_flag, N * sizeof(uint8_t)));
     CKE(cudaMalloc(&e->d_env, N * sizeof(EnvState)));
-    CKE(cudaMalloc(&e->d_totals, 8 * sizeof(unsigned long long)));
+    CKE(cudaMalloc(&e->d_totals, 3 * 8 * sizeof(unsigned long long)));
     CKE(cudaMalloc(&e->d_flagword, sizeof(uint32_t)));
     if (!e->tables.trans.empty()) {
         CKE(cudaMalloc(&e->d_trans, e->tables.trans.size() * sizeof(uint16_t)));
