@@ -12,7 +12,8 @@
 // One Agent object = `batch.n_agents` independent reference agents, each on its own Philox stream (n_agents = 1 is the
 // reference's single trait object).  Differences forced by the device boundary: the epsilon-decay closure is
 // Decay::sub(k) / Decay::mul(k); observations are dense indices (BlackJackEnv::obs_id gives the fxhash id);
-// `training_error` is per episode (sum of the episode's TDs) — see rlb_train_out.traj for the per-step stream.
+// With ONE agent `training_error` is the reference's vector — one TD per training step (agent.rs:98,117); with a batch
+// it is per episode (the sum of the episode's TDs), n_agents * n_episodes entries.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -350,16 +351,28 @@ class Agent {
         std::vector<rlb_episode_f32> e32;
         if (cfg_.real_kind == RLB_REAL_F64) { e64.resize(N * n_episodes); out.episodes = e64.data(); }
         else { e32.resize(N * n_episodes); out.episodes = e32.data(); }
+        // one agent: the per-step TD stream; at most max_steps + 1 steps per episode (Blackjack: a hand holds 16 cards)
+        std::vector<double> td64;
+        std::vector<float> td32;
+        uint64_t td_n = 0;
+        if (N == 1) {
+            const uint64_t cap = n_episodes * (cfg_.env_kind == RLB_ENV_BLACKJACK ? 32u : (uint64_t)cfg_.max_steps + 1u);
+            if (cfg_.real_kind == RLB_REAL_F64) { td64.resize(cap); out.td_steps = td64.data(); }
+            else { td32.resize(cap); out.td_steps = td32.data(); }
+            out.td_capacity = cap; out.td_count = &td_n;
+        }
         check(rlb_agent_train(engine_->get(), n_episodes, eval_at, &out));
         last_ = out;
+        last_.td_steps = nullptr; last_.td_count = nullptr;
         TrainResult r;
         auto& [rew, len, err] = r;
-        rew.resize(N * n_episodes); len.resize(N * n_episodes); err.resize(N * n_episodes);
+        rew.resize(N * n_episodes); len.resize(N * n_episodes); err.resize(N == 1 ? td_n : N * n_episodes);
+        if (N == 1) for (uint64_t k = 0; k < td_n; ++k) err[k] = cfg_.real_kind == RLB_REAL_F64 ? td64[k] : (double)td32[k];
         for (uint64_t ep = 0; ep < n_episodes; ++ep)
             for (uint64_t a = 0; a < N; ++a) {   // engine layout is [episode][agent]
                 const uint64_t src = ep * N + a, dst = a * n_episodes + ep;
-                if (cfg_.real_kind == RLB_REAL_F64) { rew[dst] = e64[src].ret; len[dst] = e64[src].length; err[dst] = e64[src].td_sum; }
-                else { rew[dst] = e32[src].ret; len[dst] = e32[src].length; err[dst] = e32[src].td_sum; }
+                if (cfg_.real_kind == RLB_REAL_F64) { rew[dst] = e64[src].ret; len[dst] = e64[src].length; if (N > 1) err[dst] = e64[src].td_sum; }
+                else { rew[dst] = e32[src].ret; len[dst] = e32[src].length; if (N > 1) err[dst] = e32[src].td_sum; }
             }
         return r;
     }

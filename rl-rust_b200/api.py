@@ -359,10 +359,12 @@ class _Agent:
         """agent.rs:66-118.  Returns (reward_history, episode_length, training_error).
 
         reward_history and episode_length are the reference's vectors ([n_episodes] for one
-        agent, [n_agents, n_episodes] otherwise).  training_error is per EPISODE here — the sum
-        of the episode's temporal differences — because a per-step stream for millions of
-        agents does not fit anywhere; Engine.train(traj_capacity=...) taps the per-step TDs
-        (rlb_traj_record.td) for small runs.  raw=True returns the engine's dict instead
+        agent, [n_agents, n_episodes] otherwise).  With ONE agent training_error is the reference's
+        too: one temporal difference per training step, episodes concatenated (agent.rs:98,117;
+        rlb_train_out.td_steps).  With a batch of agents it is per EPISODE — the sum of the
+        episode's temporal differences, [n_agents, n_episodes] — because a per-step stream for
+        millions of agents does not fit anywhere; Engine.train(td_capacity=...) returns the
+        per-step streams of small batches.  raw=True returns the engine's dict instead
         (per-episode sums over agents, step counters, kernel time).
         """
         if eval_at == 0:
@@ -371,8 +373,13 @@ class _Agent:
         if raw:
             return self.engine.train(n_episodes, eval_at)
         if self.n_agents == 1:
-            res = self.engine.train(n_episodes, eval_at, sums=False, episodes=True)
+            # the most steps n episodes can take: max_steps + 1 each (Blackjack: a hand holds 16 cards, blackjack.rs:32-35)
+            cap = int(n_episodes) * (32 if env.kind == abi.ENV_BLACKJACK else int(self.engine.cfg.max_steps) + 1)
+            res = self.engine.train(n_episodes, eval_at, sums=False, episodes=True, td_capacity=cap if cap * 8 <= (1 << 31) else 0)
             ep = res["episodes"][:, 0]
+            if "td_steps" in res:
+                n = int(res["td_count"][0])
+                return ep["ret"].astype(np.float64), ep["length"].astype(np.uint64), res["td_steps"][0, :n].astype(np.float64)
             return ep["ret"].astype(np.float64), ep["length"].astype(np.uint64), ep["td_sum"].astype(np.float64)
         res = self.engine.train(n_episodes, eval_at, sums=False, episodes=True)
         ep = res["episodes"]

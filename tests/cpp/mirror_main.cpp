@@ -109,6 +109,16 @@ int main(int argc, char** argv) {
             show("taxi", e1); show("frozen_lake", e2_); show("cliff_walking", e3_); show("blackjack", e4_);
             try { other.example(cliff, sink); std::printf("D no-throw\n"); } catch (const std::logic_error&) { std::printf("D example with 2 agents -> logic_error\n"); }
         }
+        // --- the reference's single trait object: ONE agent, training_error per STEP (agent.rs:98,117)
+        {
+            TaxiEnv taxi1(100);
+            Batch b5;
+            b5.n_agents = 1; b5.seed = 0x51;
+            UniformEpsilonGreed eg5(1.0, Decay::sub(1.0 / (0.5 * 25.0)), 0.0);
+            ElegibilityTracesAgent solo(policy, 0.95, eg5, 0.5, qlearning, b5);
+            auto [r5, l5, e5] = solo.train(taxi1, 25, 5);
+            dump("E.lengths", l5); dump("E.errors", e5);
+        }
     } catch (const std::exception& e) {
         std::printf("FAILED: %s\n", e.what());
         return 1;

@@ -39,7 +39,7 @@ def test_mirror_results_equal_oracle():
     out = subprocess.check_output([EXE], text=True)
     assert "FAILED" not in out and "no-throw" not in out
     assert "A eval_at==0 -> domain_error" in out and "A step after termination -> EnvNotReady" in out
-    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l[0] in "ABC" and "." in l.split()[0]}
+    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l[0] in "ABCE" and "." in l.split()[0]}
     n = 60
     cfg = O.make_config(O.ENV_TAXI, target=O.TARGET_QLEARNING, eps_decay=1.0 / (0.5 * n), seed=0xC0DE)
     sessions = [O.Session(cfg, i) for i in range(3)]
@@ -86,6 +86,12 @@ def test_mirror_results_equal_oracle():
         r, l, t, _ = s.train(5, 5)
         assert np.array_equal(after[i], l)
         s.close()
+    # E: one agent -> training_error is the reference's per-step vector
+    s = O.Session(O.make_config(O.ENV_TAXI, agent=O.AGENT_TRACES, target=O.TARGET_QLEARNING, eps_decay=1.0 / (0.5 * 25), seed=0x51), 0)
+    r, l, t, _ = s.train(25, 5)
+    assert np.array_equal(np.array(lines["E.lengths"], np.uint64), l)
+    assert len(lines["E.errors"]) == int(l.sum()) and P.bits_equal(f64s(lines["E.errors"]), s.training_error())
+    s.close()
     # D: Agent::example / Env::render through the C++ mirror equal the transcript built from the oracle (the same helper
     # the Python mirror's test uses) — four envs, one untrained episode each
     import importlib

@@ -39,6 +39,26 @@ def test_moving_average_is_sequential():
     assert drv.moving_average(0, v) == []      # the reference would loop forever on a zero window (utils.rs:81-90)
 
 
+def test_training_error_curve_forms():
+    """bin/taxi.rs:170-174 on the per-step stream (one agent: exact; several: mean of each agent's own curve), and the
+    per-episode fallback when the stream was not taken."""
+    drv = importlib.import_module("rl-rust_b200.driver")
+    rng = np.random.default_rng(9)
+    td = rng.standard_normal((2, 57))
+    one = dict(td_steps=td[:1], td_count=np.array([50], np.uint64), sums=np.zeros((5, 4)))
+    curve, kind = drv.training_error_curve(one, 1, 10, 1)
+    assert kind.startswith("per-step (exact") and P_bits_equal(curve, sequential_moving_average(50 // 10, td[0, :50]))
+    two = dict(td_steps=td, td_count=np.array([50, 57], np.uint64), sums=np.zeros((5, 4)))
+    curve, kind = drv.training_error_curve(two, 2, 10, 1)
+    a, b = sequential_moving_average(5, td[0, :50]), sequential_moving_average(5, td[1, :57])
+    assert len(curve) == max(len(a), len(b)) == 12 and curve[0] == (a[0] + b[0]) / 2 and curve[-1] == b[-1]
+    sums = np.array([[10.0, 0, 5.0, 0], [20.0, 0, -4.0, 0], [0.0, 0, 0.0, 0]])
+    curve, kind = drv.training_error_curve(dict(sums=sums), 3, 10, 2)
+    assert kind.startswith("per-episode") and curve[0] == (0.5 - 0.2) / 2 and np.isnan(curve[1])
+    overflow = dict(td_steps=td[:1, :20], td_count=np.array([50], np.uint64), sums=sums)   # stream cut short: fall back
+    assert drv.training_error_curve(overflow, 1, 10, 2)[1].startswith("per-episode")
+
+
 def test_moving_average_quirk():
     drv = importlib.import_module("rl-rust_b200.driver")
     v = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0]
