@@ -331,12 +331,13 @@ def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_
         t_wall0 = time.perf_counter()
         ev0.record(stream)
         for _ in range(steps):
-            step()
+            step(wait=False)                                    # asynchronous calls, at most two in flight: launches back to back
         for s_ in group_streams[1:] if n_groups > 1 else []:
             stream.wait_stream(s_)
         ev1.record(stream)
         job.barrier()
         t_wall = time.perf_counter() - t_wall0
+        drain(count=True)
         clocks = sampler.stop()
         ms = ev0.elapsed_time(ev1)
         slowed = float(any(r in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown") for r in clocks.get("reasons", [])))

@@ -93,6 +93,7 @@ struct rlb_engine {
         cudaEvent_t copies_done = nullptr;           // after its last record copy on the copy stream (pipelined calls)
         unsigned long long* h_totals = nullptr;      // pinned [8]
         bool pipelined = false;
+        bool host_records = false;                   // the call copies per-agent records to a host buffer
         rlb_traj_record* d_traj = nullptr; uint64_t* d_traj_count = nullptr; bool own_traj = false, own_count = false;
         void* d_td = nullptr; uint64_t* d_td_count = nullptr; bool own_td = false, own_td_count = false;
     };
@@ -491,8 +492,15 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
         // (each extra launch costs its tail: the last CTAs of a 32 768-CTA grid run on a mostly idle GPU).
         if (pipelined) chunk = std::max<uint64_t>(1, std::min<uint64_t>((chunk + 1) / 2, async_call ? total : (total + 3) / 4));
     }
-    // A call may only overlap the one before it when both stream records through the same two scratch halves.
-    if (!e->pending.empty() && !(pipelined && e->pending.back().pipelined && chunk == e->last_pipeline_chunk && 3 * total <= e->sums_cap / (4 * sizeof(double)))) {
+    // A call may overlap the one before it when both stream records through the same two scratch halves — or when
+    // neither sends records to the host at all: then everything either call does is in main-stream order (the record
+    // scratch is written by call i + 1's kernel only after call i's reduction has read it), and the blocks of totals
+    // and sums are per call.
+    const bool sums_fit = 3 * total * 4 * sizeof(double) <= e->sums_cap && (size_t)chunk * N * rec <= e->episodes_cap;
+    const bool both_pipelined = pipelined && !e->pending.empty() && e->pending.back().pipelined && chunk == e->last_pipeline_chunk;
+    const bool host_rec = rec_host && !is_device_ptr(rec_host);
+    const bool both_on_device = !host_rec && !e->pending.empty() && !e->pending.back().pipelined && !e->pending.back().host_records;
+    if (!e->pending.empty() && !((both_pipelined || both_on_device) && (sums_fit || !want_records))) {
         rlb_status st = finish_pending(e);
         if (st != RLB_OK) return st;
     }
@@ -511,6 +519,7 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
     double* const d_sums_call = e->d_sums + (want_records ? slot * total * 4 : 0);
     rlb_engine::Pending pd;
     pd.mode = mode; pd.out = out; pd.eval_steps_out = eval_steps_out; pd.pipelined = pipelined;
+    pd.host_records = host_rec;
     if (e->totals_pool.empty()) {
         unsigned long long* h = nullptr;
         CK(cudaHostAlloc(&h, 8 * sizeof(unsigned long long), cudaHostAllocDefault));

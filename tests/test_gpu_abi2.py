@@ -76,6 +76,28 @@ def test_async_train_equals_blocking(c):
     assert np.array_equal(st["rng_n"], ref["state"]["rng_n"])
 
 
+@pytest.mark.parametrize("c", [CASES[1], CASES[3]], ids=P.combo_id)
+def test_async_device_resident_calls_overlap(c):
+    """Asynchronous calls whose outputs stay on the device are queued back to back (two in flight, per-call blocks of
+    totals and sums): same sums, totals and tables as the blocking calls."""
+    import torch
+    n_agents, n_ep, eval_at, chunk = 500, 40, 10, 8
+    h = P.hyper(n_ep)
+    ref = P.gpu_run(c, h, n_agents, n_ep, eval_at)
+    with P.make_engine(c, h, n_agents) as eng:
+        sums = [torch.zeros((chunk, 4), dtype=torch.float64, device="cuda") for _ in range(n_ep // chunk)]
+        for k in range(n_ep // chunk):
+            eng.train((k + 1) * chunk, eval_at, ep_begin=k * chunk, sums_out=sums[k], wait=False)
+        done = eng.train_wait()
+        torch.cuda.synchronize()
+        q, counts = eng.download_tables()
+        st = eng.states()
+    assert [d["train_steps"] for d in done] == [int(ref["len"][:, k * chunk:(k + 1) * chunk].sum()) for k in range(n_ep // chunk)]
+    assert sum(d["eval_steps"] for d in done) == ref["eval_steps"]
+    assert P.bits_equal(torch.cat(sums).cpu().numpy(), ref["sums"])
+    assert P.bits_equal(q.astype(np.float64), ref["q"]) and np.array_equal(st["rng_n"], ref["state"]["rng_n"])
+
+
 @pytest.mark.parametrize("c", [CASES[0], CASES[2], CASES[3], CASES[4]], ids=P.combo_id)
 def test_agent_step_reproduces_the_loop(c):
     """A host loop over rlb_agent_step == env.reset / get_action / env.step / get_action / update driven through the
