@@ -360,6 +360,10 @@ def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_
             b0 = torch.zeros((chunk, N, rec_size // 4), dtype=torch.int32).pin_memory()
             host_recs.append([b0, torch.zeros_like(b0).pin_memory() if double_buf else b0])
         host_gath = [torch.zeros((world, chunk, 4), dtype=torch.float64).pin_memory() for _ in cells] if (world > 1 and rank == 0) else None
+        # the e2e leg times the SAME chunks of the run as the device leg did (episode lengths, hence steps per second,
+        # change along a run): untimed steps bring the chunk index back to where the device leg started
+        while state["k"] % chunks_per_run != warmup % chunks_per_run:
+            step(count=False)
         reset_acc()
         job.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -373,7 +377,7 @@ def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_
             stream.wait_stream(s_)
         e1.record(stream)
         job.barrier()
-        e2e = {"ms": e0.elapsed_time(e1), "train_steps": acc["train_steps"],
+        e2e = {"ms": e0.elapsed_time(e1), "train_steps": acc["train_steps"], "kernel_ms": acc["kernel_ms"],
                "d2h": len(cells) * (rec_bytes + chunk * 32 + 64) + (len(cells) * world * chunk * 32 if (world > 1 and rank == 0) else 0),
                "h2d": 24 * len(cells), "double_buf": double_buf}
         del host_recs
@@ -442,7 +446,8 @@ def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_
                              "hbm_frac = ncu dram bytes / launch time / measured HBM copy bandwidth"},
     }
     if e2e:
-        rec["e2e"] = {"value": e2e_steps / (e2e_ms_max * 1e-3), "unit": "agent-steps/s",
+        rec["e2e"] = {"value": e2e_steps / (e2e_ms_max * 1e-3), "unit": "agent-steps/s", "ms_per_step": e2e_ms_max / max(1, steps),
+                      "kernel_ms_per_step": e2e["kernel_ms"] / max(1, steps),
                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                       "note": "C-ABI rlb_agent_train_range_async with pinned HOST buffers: per-agent episode records + per-episode sums copied "
                               "device->host every step (%s; the last copy is waited for inside the timed region); the path has no per-step "
@@ -476,7 +481,7 @@ def main():
     ap.add_argument("--sub", default=None,
                     help="comma-separated sub-records to add under `workloads` (c4, c3, c2_f64, c1, c5, dyna); default: "
                          "'c4,c3,c2_f64' for the default headline run, none when --workload / --agents-per-gpu / --real is given")
-    ap.add_argument("--sub-steps", type=int, default=5)
+    ap.add_argument("--sub-steps", type=int, default=10, help="timed steps of each sub-record (10 = one whole 1000-episode run)")
     ap.add_argument("--sub-warmup", type=int, default=3)
     args = ap.parse_args()
     W = _workloads()
