@@ -187,7 +187,11 @@ typedef struct rlb_train_out {
     uint64_t* td_count;
 } rlb_train_out;
 
-/* Complete per-agent resumable state besides the tables. */
+/* Per-agent resumable state besides the tables — complete AT AN EPISODE BOUNDARY, which is where rlb_agent_train /
+ * rlb_agent_evaluate leave every agent.  Not part of it: the env state inside an episode (position, step counter,
+ * Blackjack hands; rlb_set_agent_states leaves env_ready alone) and a non-empty eligibility trace — a snapshot taken in
+ * the middle of an episode driven through the step-level calls does not resume that episode.  rlb_set_agent_states
+ * refuses an odd rng_n on the envs that only draw 64-bit values (every env but Blackjack). */
 typedef struct rlb_agent_state {
     double epsilon;              /* uniform_epsilon_greed.rs:13 */
     uint64_t ucb_t;              /* upper_confidence_bound.rs:12 */
@@ -336,7 +340,9 @@ rlb_status rlb_set_agent_states(rlb_engine* e, const rlb_agent_state* states /* 
  *   - one process per GPU (torchrun, MPI, a Rust launcher ...): rank 0 calls rlb_comm_unique_id(), the host side
  *     passes the 128 bytes to the other ranks by any means, every rank calls rlb_comm_init_rank();
  *   - one process driving several GPUs (one engine per device, e.g. from Rust threads): rlb_comm_init_all().
- * NCCL failures return RLB_ERR_NCCL with the NCCL error string in rlb_last_error_string(). */
+ * NCCL failures return RLB_ERR_NCCL with the NCCL error string in rlb_last_error_string().
+ * Load order: a process that also loads a library linked against a NEWER NCCL under the same soname (PyTorch) must
+ * load that library before the first rlb_comm_* call, so that the loader hands librlb the newer copy. */
 typedef struct rlb_comm rlb_comm;
 #define RLB_COMM_ID_BYTES 128
 rlb_status rlb_comm_unique_id(uint8_t id_out[RLB_COMM_ID_BYTES]);

@@ -208,25 +208,40 @@ class BlackJackEnv : public Env {   // env/blackjack.rs:30-188
 };
 class FrozenLakeEnv : public Env {   // env/frozen_lake.rs:12-134
    public:
-    enum Map { MAP_4X4 = 0, MAP_8X8 = 1 };
-    FrozenLakeEnv(Map map, bool is_slippery, uint32_t max_steps) : map_(map), slippery_(is_slippery), max_steps_(max_steps) {}
+    enum Map { MAP_4X4 = 0, MAP_8X8 = 1 };   // the crate's two constants (:23-28)
+    FrozenLakeEnv(Map map, bool is_slippery, uint32_t max_steps)
+        : rows_(map == MAP_4X4 ? std::vector<std::string>{"SFFF", "FHFH", "FFFH", "HFFG"}
+                               : std::vector<std::string>{"SFFFFFFF", "FFFFFFFF", "FFFHFFFF", "FFFFFHFF", "FFFHFFFF", "FHHFFFHF", "FHFFHFHF", "FFFHFFFG"}),
+          map_id_(map), slippery_(is_slippery), max_steps_(max_steps) {}
+    // FrozenLakeEnv::new(map: &[&str], ..) (:48): any rows of S / F / H / G cells; every 'S' is a start cell (:54-66)
+    FrozenLakeEnv(const std::vector<std::string>& map, bool is_slippery, uint32_t max_steps)
+        : rows_(map), map_id_(RLB_MAP_CUSTOM), slippery_(is_slippery), max_steps_(max_steps) {
+        if (rows_.empty()) throw std::invalid_argument("empty map");
+        for (const std::string& r : rows_) {
+            if (r.size() != rows_[0].size() || r.empty()) throw std::invalid_argument("map rows must be equally long");
+            flat_ += r;
+        }
+    }
     size_t action_size() const override { return 4; }
-    void describe(rlb_config& c) const override { c.env_kind = RLB_ENV_FROZEN_LAKE; c.map_id = map_; c.slippery = slippery_; c.max_steps = max_steps_; }
+    void describe(rlb_config& c) const override {
+        c.env_kind = RLB_ENV_FROZEN_LAKE; c.map_id = map_id_; c.slippery = slippery_; c.max_steps = max_steps_;
+        if (map_id_ == RLB_MAP_CUSTOM) { c.map_rows = (uint32_t)rows_.size(); c.map_cols = (uint32_t)rows_[0].size(); c.map = flat_.c_str(); }
+    }
     const char* get_action_label(size_t a) const override { static const char* k[] = {"LEFT", "DOWN", "RIGHT", "UP"}; return k[a]; }   // :30
 
    protected:
     uint64_t step_limit() const override { return max_steps_; }
     std::string render_at(uint32_t pos, size_t) const override {   // frozen_lake.rs:136-149: every 'S' becomes 'F', then '@'
-        static const std::vector<std::string> m4 = {"SFFF", "FHFH", "FFFH", "HFFG"};
-        static const std::vector<std::string> m8 = {"SFFFFFFF", "FFFFFFFF", "FFFHFFFF", "FFFFFHFF", "FFFHFFFF", "FHHFFFHF", "FHFFHFHF", "FFFHFFFG"};
-        std::string text = join_rows(map_ == MAP_4X4 ? m4 : m8);
+        std::string text = join_rows(rows_);
         for (char& ch : text) if (ch == 'S') ch = 'F';
         text[skip_newlines(text, pos)] = '@';
         return text;
     }
 
    private:
-    Map map_; bool slippery_; uint32_t max_steps_;
+    std::vector<std::string> rows_;
+    std::string flat_;
+    int32_t map_id_; bool slippery_; uint32_t max_steps_;
 };
 class CliffWalkingEnv : public Env {   // env/cliff_walking.rs:6-89
    public:

@@ -505,6 +505,17 @@ def blackjack_dense_index(obs_id):
     return lib.rlb_blackjack_dense_index(obs_id)
 
 
+def _nccl_load_order():
+    """librlb resolves NCCL at run time with dlopen("libnccl.so.2").  PyTorch links a NEWER NCCL under the same soname:
+    if librlb's copy (the system's) is loaded first, a later `import torch` binds to it and fails on the symbols it lacks.
+    So, where PyTorch is installed, import it BEFORE the first rlb_comm_* call — the loader then hands librlb the copy
+    PyTorch brought.  A host without PyTorch (a Rust binary) has a single NCCL and no ordering to mind."""
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
+
+
 class Comm:
     """rlb_comm: the path's one multi-GPU exchange (NCCL send/recv gather of the per-episode metric sums)."""
 
@@ -513,12 +524,14 @@ class Comm:
 
     @staticmethod
     def unique_id():
+        _nccl_load_order()
         buf = (C.c_uint8 * COMM_ID_BYTES)()
         check(lib.rlb_comm_unique_id(buf))
         return bytes(buf)
 
     @classmethod
     def init_rank(cls, unique_id, world_size, rank, device):
+        _nccl_load_order()
         buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
         h = C.c_void_p()
         check(lib.rlb_comm_init_rank(buf, world_size, rank, device, C.byref(h)))
@@ -526,6 +539,7 @@ class Comm:
 
     @classmethod
     def init_all(cls, devices):
+        _nccl_load_order()
         devs = (C.c_int32 * len(devices))(*devices)
         hs = (C.c_void_p * len(devices))()
         check(lib.rlb_comm_init_all(devs, len(devices), hs))

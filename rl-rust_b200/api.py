@@ -153,7 +153,9 @@ class BlackJackEnv(Env):
 
 
 class FrozenLakeEnv(Env):
-    """env/frozen_lake.rs:12-134.  `map` is FrozenLakeEnv.MAP_4X4 or MAP_8X8."""
+    """env/frozen_lake.rs:12-134.  `map` is any list of equally long rows of S / F / H / G cells, as
+    `FrozenLakeEnv::new(map: &[&str], ..)` takes (:48) — FrozenLakeEnv.MAP_4X4 and MAP_8X8 are the crate's two constants
+    (:23-28).  Every 'S' is a start cell (:54-66)."""
     kind = abi.ENV_FROZEN_LAKE
     COUNT = 4
     ACTIONS = ("LEFT", "DOWN", "RIGHT", "UP")
@@ -162,21 +164,21 @@ class FrozenLakeEnv(Env):
 
     def __init__(self, map, is_slippery, max_steps):
         super().__init__()
-        map = tuple(map)
-        if map == self.MAP_4X4:
-            self.map_id = 0
-        elif map == self.MAP_8X8:
-            self.map_id = 1
-        else:
-            raise ValueError("only the reference's MAP_4X4 / MAP_8X8 are supported")
+        self.map = tuple(str(r) for r in map)
+        if not self.map or any(len(r) != len(self.map[0]) or set(r) - set("SFHG") for r in self.map):
+            raise ValueError("map rows must be non-empty, equally long and made of S, F, H, G")
+        self.map_id = 0 if self.map == self.MAP_4X4 else (1 if self.map == self.MAP_8X8 else abi.MAP_CUSTOM)
         self.is_slippery = bool(is_slippery)
         self.max_steps = int(max_steps)
 
     def _cfg(self):
-        return dict(map_id=self.map_id, slippery=self.is_slippery, max_steps=self.max_steps)
+        cfg = dict(map_id=self.map_id, slippery=self.is_slippery, max_steps=self.max_steps)
+        if self.map_id == abi.MAP_CUSTOM:
+            cfg["map_rows"] = list(self.map)
+        return cfg
 
     def _render_state(self, pos, agent):   # frozen_lake.rs:136-149
-        return _render.render_frozen_lake(self.MAP_4X4 if self.map_id == 0 else self.MAP_8X8, pos)
+        return _render.render_frozen_lake(self.map, pos)
 
 
 class CliffWalkingEnv(Env):

@@ -109,6 +109,16 @@ int main(int argc, char** argv) {
             show("taxi", e1); show("frozen_lake", e2_); show("cliff_walking", e3_); show("blackjack", e4_);
             try { other.example(cliff, sink); std::printf("D no-throw\n"); } catch (const std::logic_error&) { std::printf("D example with 2 agents -> logic_error\n"); }
         }
+        // --- FrozenLakeEnv::new on the caller's own rows (frozen_lake.rs:48): two start cells, 5 x 7
+        {
+            FrozenLakeEnv lake2(std::vector<std::string>{"SFFFFFH", "FFHFFFF", "FFFFHFS", "HFFFFFF", "FFFHFFG"}, true, 40);
+            Batch b6;
+            b6.n_agents = 4; b6.seed = 0xF1A6;
+            UniformEpsilonGreed eg6(1.0, Decay::sub(1.0 / (0.5 * 30.0)), 0.0);
+            OneStepAgent walker(policy, 0.95, eg6, qlearning, b6);
+            auto [r6, l6, e6] = walker.train(lake2, 30, 10);
+            dump("F.lengths", l6); dump("F.rewards", r6);
+        }
         // --- the reference's single trait object: ONE agent, training_error per STEP (agent.rs:98,117)
         {
             TaxiEnv taxi1(100);

@@ -39,7 +39,7 @@ def test_mirror_results_equal_oracle():
     out = subprocess.check_output([EXE], text=True)
     assert "FAILED" not in out and "no-throw" not in out
     assert "A eval_at==0 -> domain_error" in out and "A step after termination -> EnvNotReady" in out
-    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l[0] in "ABCE" and "." in l.split()[0]}
+    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l[0] in "ABCEF" and "." in l.split()[0]}
     n = 60
     cfg = O.make_config(O.ENV_TAXI, target=O.TARGET_QLEARNING, eps_decay=1.0 / (0.5 * n), seed=0xC0DE)
     sessions = [O.Session(cfg, i) for i in range(3)]
@@ -86,6 +86,12 @@ def test_mirror_results_equal_oracle():
         r, l, t, _ = s.train(5, 5)
         assert np.array_equal(after[i], l)
         s.close()
+    # F: a caller-supplied FrozenLake map through the mirror's FrozenLakeEnv(rows, ..) constructor
+    rows = ["SFFFFFH", "FFHFFFF", "FFFFHFS", "HFFFFFF", "FFFHFFG"]
+    cf = dict(env=1, agent=0, selector=0, policy=0, target=1, real=1)
+    of = O.batch_train(P.oracle_config(cf, P.hyper(30, seed=0xF1A6, max_steps=40, map_rows=rows)), 0, 4, 30, 10, n_threads=2)
+    assert np.array_equal(np.array(lines["F.lengths"], np.uint64).reshape(4, 30), of["len"])
+    assert P.bits_equal(f64s(lines["F.rewards"]).reshape(4, 30), of["ret"])
     # E: one agent -> training_error is the reference's per-step vector
     s = O.Session(O.make_config(O.ENV_TAXI, agent=O.AGENT_TRACES, target=O.TARGET_QLEARNING, eps_decay=1.0 / (0.5 * 25), seed=0x51), 0)
     r, l, t, _ = s.train(25, 5)

