@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight Systems / Compute timelines, no-ops otherwise
+
 #include "rlb_host.h"
 #include "rlb_launch.h"
 #include "rlb_step_kernels.cuh"
@@ -564,7 +566,15 @@ rlb_status enqueue_range(rlb_engine* e, int mode, uint64_t begin, uint64_t end, 
         if (!ev0 || !ev1) { set_error("cudaEventCreate failed"); return RLB_ERR_CUDA; }
         pd.events.push_back(ev0); pd.events.push_back(ev1);
         CK(cudaEventRecord(ev0, e->stream));
-        CK(dispatch_run(e, p));
+        {
+            char label[96];
+            snprintf(label, sizeof label, "rlb %s env=%d agents=%llu episodes=[%llu,%llu)", mode == 0 ? "train" : "evaluate", e->cfg.env_kind,
+                     (unsigned long long)N, (unsigned long long)c0, (unsigned long long)c1);
+            nvtxRangePushA(label);
+            cudaError_t lerr = dispatch_run(e, p);
+            nvtxRangePop();
+            if (lerr != cudaSuccess) return cuda_fail(lerr, "k_run launch");
+        }
         CK(cudaEventRecord(ev1, e->stream));
         const uint64_t n_ep = c1 - c0;
         if (sums_dst) {   // reads the records on the main stream, before that scratch is written again

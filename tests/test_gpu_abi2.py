@@ -49,12 +49,13 @@ def test_td_stream_is_training_error(c):
         assert P.bits_equal(b["td_steps"][i, :min(nb, 3)].astype(np.float64), refs[i][na:na + min(nb, 3)])
 
 
+@pytest.mark.parametrize("chunk", [16, 4])   # 16: records stream through the two scratch halves; 4: too short to pipeline
 @pytest.mark.parametrize("c", [CASES[1], CASES[2]], ids=P.combo_id)
-def test_async_train_equals_blocking(c):
+def test_async_train_equals_blocking(c, chunk):
     """rlb_agent_train_range_async + rlb_agent_train_wait: same records, sums, totals and tables as the blocking call,
     with two calls in flight and pinned host record buffers (the pipelined copy path)."""
     import torch
-    n_agents, n_ep, eval_at, chunk = 300, 48, 12, 16
+    n_agents, n_ep, eval_at = 300, 48, 12
     h = P.hyper(n_ep)
     ref = P.gpu_run(c, h, n_agents, n_ep, eval_at)
     with P.make_engine(c, h, n_agents) as eng:
