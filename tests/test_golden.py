@@ -49,6 +49,45 @@ def test_engine_reproduces_golden(key):
     check(key, res)
 
 
+# ---- round-2 features (tests/golden/golden_v2.npz, made by tests/golden/make_golden_v2.py): caller-supplied FrozenLake
+# maps and the per-step training_error vector
+import make_golden_v2 as G2   # noqa: E402
+
+GOLD2 = np.load(os.path.join(HERE, "golden", "golden_v2.npz"))
+KEYS2 = sorted({k.split("/")[0] for k in GOLD2.files})
+
+
+def check2(key, res, tds):
+    assert np.array_equal(res["len"].astype(np.uint32), GOLD2[key + "/len"])
+    assert P.bits_equal(res["ret"], GOLD2[key + "/ret"])
+    assert P.bits_equal(res["q"][:2], GOLD2[key + "/q"])
+    assert np.array_equal(res["state"]["rng_n"], GOLD2[key + "/rng_n"])
+    for i, t in enumerate(tds):
+        want = GOLD2[key + "/td%d" % i]
+        assert len(t) == len(want) == int(res["len"][i].sum()) and P.bits_equal(np.asarray(t, np.float64), want)
+
+
+@pytest.mark.parametrize("key", KEYS2)
+def test_oracle_reproduces_golden_v2(key):
+    name, real = key.rsplit("_", 1)
+    o = G2.run_case(G2.CASES[name], 1 if real == "f64" else 0)
+    check2(key, o, o["td"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", KEYS2)
+def test_engine_reproduces_golden_v2(key):
+    name, real = key.rsplit("_", 1)
+    case = G2.CASES[name]
+    c = dict(case["c"], real=1 if real == "f64" else 0)
+    h = G2.hyper_of(case)
+    res = P.gpu_run(c, h, G2.N_AGENTS, G2.N_EPISODES, G2.EVAL_AT, first_agent_id=G2.FIRST_AGENT)
+    with P.make_engine(c, h, G2.TD_AGENTS, G2.FIRST_AGENT) as eng:
+        r = eng.train(G2.N_EPISODES, G2.EVAL_AT, td_capacity=G2.N_EPISODES * 41)
+    tds = [r["td_steps"][i, :int(r["td_count"][i])] for i in range(G2.TD_AGENTS)]
+    check2(key, res, tds)
+
+
 # ---- `Agent::example` transcripts (tests/golden/example_v1.json, made by tests/golden/make_example_golden.py)
 import json   # noqa: E402
 
