@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 # (case, combination, hyper-parameter overrides, bound on the worst cell's relative error among cells above 1e-3 of the
 # largest |Q|).  Against the largest |Q| every case is held to the north star's 1e-6.  Measured on a B200
-# (profiles/r02l_f32_vs_f64.txt): Taxi Q-learning 1.8e-7 per cell / 4.8e-8 of scale after 29 158 updates, CliffWalking
+# (profiles/r02o_f32_vs_f64.txt): Taxi Q-learning 1.8e-7 per cell / 4.8e-8 of scale after 29 158 updates, CliffWalking
 # 3.0e-7 / 3.5e-8, Blackjack 9.5e-7 / 5.9e-8 (its values are sums of +-1 that cancel: small cells), Taxi Q(lambda)
 # 1.3e-6 / 2.3e-7 (a trace sweep applies lr * (td * e) to every visited row at every step: ~50x the roundings).
 CASES = [
