@@ -386,7 +386,7 @@ def measure(job, args, name, w, real, steps, warmup, with_e2e, cpu_agents, cell_
     ms_max, e2e_ms_max, kernel_ms_max = job.allreduce([ms, e2e["ms"] if e2e else 0.0, dev["kernel_ms"]], "max")
     train_steps, eval_steps, e2e_steps, trace_rows, agents_total = job.allreduce(
         [dev["train_steps"], dev["eval_steps"], e2e["train_steps"] if e2e else 0, dev["trace_rows"], N * len(cells)], "sum")
-    store = {1: "hbm", 2: "shared_memory_groups", 3: "hybrid_smem_q_l2_traces"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)]
+    store = {1: "hbm", 2: "shared_memory_groups", 3: "hybrid_smem_q_l2_traces", 4: "hbm_lazy_trace_sweeps"}[rlb.abi.lib.rlb_engine_store_kind(eng.h)]
     for e_ in engines:
         e_.close()
     if rank != 0:

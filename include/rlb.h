@@ -123,7 +123,8 @@ typedef struct rlb_config {
     uint64_t n_agents;           /* agents held by this engine */
     uint64_t first_agent_id;     /* global id of local agent 0 (Philox counter high words) */
     uint32_t store_kind;         /* where the fused kernel keeps the tables: 0 = auto, 1 = HBM, 2 = shared memory (one agent per
-                                    4-lane thread group), 3 = hybrid (Q in shared memory, eligibility rows streamed through L2) */
+                                    4-lane thread group), 3 = hybrid (Q in shared memory, eligibility rows streamed through L2),
+                                    4 = HBM with a trace agent's sweeps applied lazily (same results, row by row on demand) */
     uint32_t planning_steps;     /* > 0: the agent is wrapped as InternalModelAgent::new(agent, RandomModel::default(), planning_steps)
                                     (agent/internal_model_agent.rs:17-29; bin/cliffwalking_model.rs:150-156 passes 10).  Needs the HBM store. */
     /* FrozenLakeEnv::new(map: &[&str], ..) (frozen_lake.rs:48) with a caller-supplied map: map_id = RLB_MAP_CUSTOM and
@@ -217,7 +218,7 @@ rlb_status rlb_engine_set_stream(rlb_engine* e, void* cuda_stream);
 rlb_status rlb_engine_synchronize(rlb_engine* e);
 /* Env::action_size (env.rs:20-22) and the dense observation count */
 rlb_status rlb_engine_dims(const rlb_engine* e, uint32_t* n_states, uint32_t* n_actions, uint32_t* n_tables);
-/* which table store the engine picked (1 HBM, 2 shared memory thread groups, 3 hybrid) */
+/* which table store the engine picked (1 HBM, 2 shared memory thread groups, 3 hybrid, 4 HBM + lazy trace sweeps) */
 uint32_t rlb_engine_store_kind(const rlb_engine* e);
 
 /* ---- Env<T,COUNT> (env.rs:19-49), batched ------------------------------------------------ */

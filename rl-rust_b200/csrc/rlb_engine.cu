@@ -7,6 +7,7 @@
 // k_episode_sums reduces.  There is no CPU path: every compute entry point needs a device.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -83,6 +84,9 @@ struct rlb_engine {
     uint32_t* d_cur_obs = nullptr;
     uint32_t* d_cur_action = nullptr;
     void* h_step_stage = nullptr; size_t step_stage_cap = 0;   // rlb_agent_step: mapped pinned block for host outputs
+    uint8_t* d_lz_slot = nullptr;      // lazy trace sweeps: row key -> slot candidate [N][S]
+    uint8_t* d_lz_tmat = nullptr;      //                    sweeps applied per slot  [N][VMAX]
+    uint32_t d_lz_tmat_rows = 0;
     double* d_log_table = nullptr;     // ln(t) for t < RLB_LOG_TABLE_N (UCB), filled on the device by portable_log
     // Calls whose work is enqueued but not yet waited for (rlb_agent_train_range_async): at most two, so that the
     // kernels of call i + 1 are in the queue before the host blocks on the copies of call i.
@@ -221,6 +225,9 @@ rlb_status pick_store(rlb_engine* e) {
         if (e->variant.trace) {
             if (fits_hybrid && 3 * (b_hybrid + 1024) <= per_sm) want = STORE_HYBRID;   // f64 C2 at 3 CTAs/SM: 4.2e9 vs 3.4e9 (groups, HBM)
             else if (fits_group && 4 * (b_group + 1024) <= per_sm) want = STORE_SMEM;
+            // tables too big for the chip: HBM, and the sweeps applied lazily where episodes are long (Taxi: 10-12 rows
+            // swept per step; Blackjack's 1.5 rows per step are cheaper swept as they come — profiles/r02s_lazy_phase.txt)
+            else if (e->dp.vmax <= 255 && e->cfg.env_kind != RLB_ENV_BLACKJACK) want = STORE_LAZY;
         }
     } else if (want == STORE_SMEM && !fits_group) {
         set_error("store_kind = shared memory (thread groups): needs %zu bytes per 8 agents (max %zu) or the env is not compiled for it", b_group, per_block_max);
@@ -228,6 +235,31 @@ rlb_status pick_store(rlb_engine* e) {
     } else if (want == STORE_HYBRID && !fits_hybrid) {
         set_error("store_kind = hybrid: needs %zu bytes per 32 agents (max %zu) or the env is not compiled for it", b_hybrid, per_block_max);
         return RLB_ERR_UNSUPPORTED;
+    }
+    if (want == STORE_LAZY) {
+        if (!e->variant.trace) { set_error("store_kind = lazy sweeps is for eligibility-trace agents"); return RLB_ERR_UNSUPPORTED; }
+        if (e->dp.vmax > 255) { set_error("store_kind = lazy sweeps: more than 255 eligibility rows per agent"); return RLB_ERR_UNSUPPORTED; }
+        // TD history per agent: one value per sweep of an episode (max_steps + 1; Blackjack: a hand holds 16 cards), capped by
+        // 64 KB of shared memory per 128-agent CTA — a longer episode brings every row up to date when the history is full
+        const uint64_t by_steps = e->cfg.env_kind == RLB_ENV_BLACKJACK ? 32ull : (uint64_t)e->cfg.max_steps + 1ull;
+        const uint64_t by_smem = (64u * 1024u) / (128u * e->real_size);
+        e->dp.lz_cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(by_steps, by_smem), 255));
+        if (const char* t = getenv("RLB_LZ_CAP")) {   // tuning override (tools/lazy_phase.py): sweeps between two full updates of the rows
+            const long v = atol(t);
+            if (v >= 1) e->dp.lz_cap = (uint32_t)std::min<uint64_t>((uint64_t)v, e->dp.lz_cap);
+        }
+        const uint64_t N = e->cfg.n_agents;
+        if (!e->d_lz_slot) {
+            CK(cudaMalloc(&e->d_lz_slot, (size_t)N * e->S));
+            CK(cudaMemsetAsync(e->d_lz_slot, 0, (size_t)N * e->S, e->stream));
+        }
+        if (e->d_lz_tmat_rows < e->dp.vmax) {
+            if (e->d_lz_tmat) cudaFree(e->d_lz_tmat);
+            CK(cudaMalloc(&e->d_lz_tmat, (size_t)N * e->dp.vmax));
+            CK(cudaMemsetAsync(e->d_lz_tmat, 0, (size_t)N * e->dp.vmax, e->stream));
+            e->d_lz_tmat_rows = e->dp.vmax;
+        }
+        e->dp.lz_slot = e->d_lz_slot; e->dp.lz_tmat = e->d_lz_tmat;
     }
     e->store = want;
     e->smem_bytes = want == STORE_SMEM ? b_group : (want == STORE_HYBRID ? b_hybrid : 0);
@@ -386,7 +418,7 @@ bool valid_cfg(const rlb_config* c) {
         c->target_kind > 2 || c->agent_kind < 0 || c->agent_kind > 1 || c->real_kind < 0 || c->real_kind > 1 ||
         c->decay_kind < 0 || c->decay_kind > 1) { set_error("enum field out of range"); return false; }
     if (c->n_agents == 0) { set_error("n_agents must be > 0"); return false; }
-    if (c->store_kind > 3) { set_error("store_kind out of range"); return false; }
+    if (c->store_kind > 4) { set_error("store_kind out of range"); return false; }
     return true;
 }
 
@@ -707,6 +739,7 @@ rlb_status rlb_engine_create(const rlb_config* cfg, rlb_engine** out) {
     p.cur_obs = nullptr; p.cur_action = nullptr;
     p.fl_start = e->tables.fl_start;
     p.log_table = nullptr; p.log_table_n = 0;
+    p.lz_slot = nullptr; p.lz_tmat = nullptr; p.lz_cap = 0;
     p.model_ent = nullptr; p.model_bits = nullptr; p.model_len = nullptr; p.planning_steps = 0; p.mcap = 0; p.mwords = 0;
 
     CKE(fill_q_default(e));
@@ -736,6 +769,8 @@ void rlb_engine_destroy(rlb_engine* e) {
     if (e->d_cur_obs) cudaFree(e->d_cur_obs);
     if (e->d_cur_action) cudaFree(e->d_cur_action);
     if (e->d_log_table) cudaFree(e->d_log_table);
+    if (e->d_lz_slot) cudaFree(e->d_lz_slot);
+    if (e->d_lz_tmat) cudaFree(e->d_lz_tmat);
     if (e->h_step_stage) cudaFreeHost(e->h_step_stage);
     void* bufs[] = {e->d_q, e->d_counts, e->d_etr, e->d_etr_il, e->d_vis, e->d_nvis, e->d_rng_n, e->d_eps, e->d_ucb_t, e->d_flag, e->d_env,
                     e->d_trans, e->d_thr, e->d_thr_state, e->d_totals, e->d_flagword, e->d_episodes, e->d_sums,

@@ -109,6 +109,20 @@ cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStre
     }
     const unsigned grid = grid_for(p.n_agents);
     const size_t smem = EnvTab<ENV>::smem_bytes(p.S);
+    if (store == STORE_LAZY) {   // trace agents, HBM tables, sweeps applied lazily: + the TD history in shared memory
+        if (!v.trace) return cudaErrorInvalidValue;
+        const size_t hist = ((smem + 15) & ~(size_t)15) + (size_t)p.lz_cap * kBlock * (v.real == RLB_REAL_F32 ? 4 : 8);
+#define RLB_CALL(R, P, SL, T)                                                                                          \
+    if constexpr (T) {                                                                                                 \
+        auto kern = k_run<ENV, R, P, SL, true, STORE_LAZY>;                                                            \
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist);          \
+        if (err != cudaSuccess) return err;                                                                            \
+        kern<<<grid, kBlock, hist, stream>>>(p);                                                                       \
+    }
+        RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
+        return cudaGetLastError();
+    }
 #define RLB_CALL(R, P, SL, T)                                                   \
     {                                                                           \
         auto kern = k_run<ENV, R, P, SL, T, STORE_GLOBAL>;                      \
@@ -146,6 +160,12 @@ cudaError_t run_kernel_attributes(const Variant& v, int store, cudaFuncAttribute
             RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
         }
+        return cudaErrorInvalidValue;
+    }
+    if (store == STORE_LAZY) {
+#define RLB_CALL(R, P, SL, T) if constexpr (T) return cudaFuncGetAttributes(attr, k_run<ENV, R, P, SL, true, STORE_LAZY>)
+        RLB_VARIANT_SWITCH(v, RLB_CALL)
+#undef RLB_CALL
         return cudaErrorInvalidValue;
     }
 #define RLB_CALL(R, P, SL, T) return cudaFuncGetAttributes(attr, k_run<ENV, R, P, SL, T, STORE_GLOBAL>)

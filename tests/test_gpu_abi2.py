@@ -274,3 +274,54 @@ def test_comm_gather_single_process(rlb):
         comms[0].gather_episode_sums(local[0], out, root=5)
     for cm in comms:
         cm.close()
+
+
+@pytest.mark.parametrize("env,real,max_steps", [(3, 1, 150), (3, 0, 250), (1, 1, 100), (0, 0, 100), (2, 1, 90)])
+@pytest.mark.parametrize("policy,selector,target", [(0, 0, 0), (1, 0, 1), (1, 1, 2), (0, 1, 1)])
+def test_lazy_trace_sweeps_equal_eager(env, real, max_steps, policy, selector, target):
+    """store_kind 4 — a trace agent's sweeps recorded and applied to a row only when it is next read or the trace is
+    cleared — against the oracle, with episodes longer than the shared-memory TD history (f64: 64 sweeps, f32: 128: the
+    history fills and every row is brought up to date mid-episode), Double tables (the write table alternates per sweep)
+    and UCB; then the step-level API leaves a trace behind and the fused kernel picks it up."""
+    c = dict(env=env, agent=1, selector=selector, policy=policy, target=target, real=real)
+    n_agents, n_ep, eval_at = 37, 16, 4
+    h = P.hyper(n_ep, max_steps=max_steps, lambda_=0.9)
+    o = O.batch_train(P.oracle_config(c, h), 0, n_agents, n_ep, eval_at, n_threads=4)
+    g = P.gpu_run(c, h, n_agents, n_ep, eval_at, store_kind=4)
+    P.compare(g, o, c)
+    if env == 3 and policy == 1 and selector == 0:
+        # a trace left by step-level update() calls carries into the fused kernel (the map survives between calls)
+        sessions = [O.Session(P.oracle_config(c, h), i) for i in range(4)]
+        with P.make_engine(c, h, 4, store_kind=4) as eng:
+            obs = eng.env_reset(); act = eng.get_action(obs)
+            ref_o = [s.env_reset() for s in sessions]; ref_a = [s.get_action(x) for s, x in zip(sessions, ref_o)]
+            for _ in range(5):
+                o2, r, t = eng.env_step(act); a2 = eng.get_action(o2)
+                eng.update(obs, act, r, t, o2, a2)
+                for k, s in enumerate(sessions):
+                    x, rr, tt = s.env_step(ref_a[k]); y = s.get_action(x)
+                    s.update(ref_o[k], ref_a[k], rr, tt, x, y)
+                    ref_o[k], ref_a[k] = x, y
+                obs, act = o2, a2
+            res = eng.train(6, 3, sums=False, episodes=True)
+            q, counts = eng.download_tables()
+        for k, s in enumerate(sessions):
+            ret, ln, tds, _ = s.train(6, 3)
+            assert np.array_equal(res["episodes"]["length"][:, k], ln)
+            assert P.bits_equal(res["episodes"]["td_sum"][:, k].astype(np.float64), tds)
+            assert P.bits_equal(q[k].astype(np.float64), s.export()[0])
+            s.close()
+
+
+def test_lazy_store_row_limit(rlb):
+    """The lazy store keeps an agent's visited-row slots in 8 bits: more than 255 possible rows per episode is refused when
+    asked for explicitly, and the automatic choice falls back to the eager HBM store."""
+    c = dict(env=3, agent=1, selector=0, policy=0, target=0, real=0)
+    h = P.hyper(8, max_steps=300)
+    with pytest.raises(rlb.RlbError) as ei:
+        P.make_engine(c, h, 8, store_kind=4)
+    assert ei.value.status == rlb.abi.ERR_UNSUPPORTED
+    with P.make_engine(c, h, 8) as eng:
+        assert eng.store_kind() == 1
+    with P.make_engine(c, P.hyper(8, max_steps=200), 8) as eng:
+        assert eng.store_kind() == 4

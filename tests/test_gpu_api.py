@@ -264,7 +264,7 @@ def test_truncation_edges(env, max_steps):
         h = P.hyper(n_ep, max_steps=max_steps)
         o = O.batch_train(P.oracle_config(c, h), 0, n_agents, n_ep, 2, n_threads=4)
         assert o["len"].max() <= max_steps + 1
-        for store in ((1, 2, 3) if env in (1, 2) else (1,)):
+        for store in ((1, 2, 3, 4) if env in (1, 2) else (1, 4)):
             g = P.gpu_run(c, h, n_agents, n_ep, 2, store_kind=store)
             P.compare(g, o, c)
 

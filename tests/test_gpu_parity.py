@@ -21,6 +21,8 @@ def test_full_matrix(c):
     o = O.batch_train(P.oracle_config(c, h), 0, N_AGENTS, N_EPISODES, EVAL_AT, n_threads=8)
     # both table stores where the env is compiled for shared memory (FrozenLake, CliffWalking); HBM otherwise
     stores = (1, 2, 3) if c["env"] in (1, 2) else (1,)
+    if c["agent"] == 1:
+        stores += (4,)   # trace agents: HBM tables with the sweeps applied lazily (what `auto` picks for Taxi and Blackjack)
     for store in stores:
         try:
             g = P.gpu_run(c, h, N_AGENTS, N_EPISODES, EVAL_AT, store_kind=store)

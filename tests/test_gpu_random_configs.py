@@ -32,7 +32,7 @@ def test_random_configuration(case):
     rng = np.random.default_rng(1000 + case)
     c, h, n_ep, eval_at, n_agents, first = draw(rng)
     o = O.batch_train(P.oracle_config(c, h), first, n_agents, n_ep, eval_at, n_threads=8)
-    for store in ((1, 2, 3) if c["env"] in (1, 2) else (1,)):
+    for store in ((1, 2, 3) if c["env"] in (1, 2) else (1,)) + ((4,) if c["agent"] == 1 else ()):
         try:
             g = P.gpu_run(c, h, n_agents, n_ep, eval_at, first_agent_id=first, store_kind=store)
         except Exception as exc:   # noqa: BLE001
