@@ -16,6 +16,9 @@ KERNELS = {
     "C3 k_run<CLIFF,f32,Double,UCB,one-step,HBM>": ("k_runILi2EfLi1ELi1ELb0ELi1ELb0E", 64, 500, 200),
     "C1 k_run<BLACKJACK,f32,Basic,eps,one-step,HBM>": ("k_runILi0EfLi0ELi0ELb0ELi1ELb0E", 64, 400, 200),
     "C2 k_run<FROZEN_LAKE,f32,Basic,eps,traces,hybrid>": ("k_runILi1EfLi0ELi0ELb1ELi3ELb0E", 255, 0, 0),
+    # C5's slowest cells: Taxi trace agents on the lazy store (eps-greedy: no launch bound; UCB: 4 CTAs/SM = 128 registers)
+    "C5 k_run<TAXI,f32,Basic,eps,traces,HBM-lazy>": ("k_runILi3EfLi0ELi0ELb1ELi4ELb0E", 168, 0, 0),
+    "C5 k_run<TAXI,f32,Double,UCB,traces,HBM-lazy>": ("k_runILi3EfLi1ELi1ELb1ELi4ELb0E", 128, 300, 128),
 }
 
 
