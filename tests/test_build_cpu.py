@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (mangled-name fragment, max registers, max spill-store bytes, max stack-frame bytes)
 KERNELS = {
     "C4 k_run<TAXI,f32,Basic,eps,one-step,HBM>": ("k_runILi3EfLi0ELi0ELb0ELi1ELb0E", 64, 400, 200),
-    "C3 k_run<CLIFF,f32,Double,UCB,one-step,HBM>": ("k_runILi2EfLi1ELi1ELb0ELi1ELb0E", 64, 500, 200),
+    "C3 k_run<CLIFF,f32,Double,UCB,one-step,HBM>": ("k_runILi2EfLi1ELi1ELb0ELi1ELb0E", 96, 300, 120),   # 5 CTAs/SM
     "C1 k_run<BLACKJACK,f32,Basic,eps,one-step,HBM>": ("k_runILi0EfLi0ELi0ELb0ELi1ELb0E", 64, 400, 200),
     "C2 k_run<FROZEN_LAKE,f32,Basic,eps,traces,hybrid>": ("k_runILi1EfLi0ELi0ELb1ELi3ELb0E", 255, 0, 0),
     # C5's slowest cells: Taxi trace agents on the lazy store (eps-greedy: no launch bound; UCB: 4 CTAs/SM = 128 registers)

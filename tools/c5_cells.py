@@ -7,9 +7,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 W = importlib.import_module("rl-rust_b200.workloads")
 w = W.WORKLOADS["c5"]; N = int(sys.argv[1]) if len(sys.argv) > 1 else 102400
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ""      # substring of the cell id, e.g. "onestep-ucb"
 rows = []
 for cell in w["cells"]:
     c = dict(w, **cell)
+    if ONLY not in W.combo_id(W.combo(c, 0)):
+        continue
     eng = W.make_engine(W.combo(c, 0), W.workload_hyper(c), N)
     sums = torch.zeros((100, 4), dtype=torch.float64, device="cuda")
     eng.train(100, 100, ep_begin=0, sums_out=sums)
