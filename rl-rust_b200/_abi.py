@@ -255,7 +255,8 @@ class Engine:
         check(lib.rlb_engine_synchronize(self.h))
 
     def store_kind(self):
-        """Which table store the fused kernel runs with: 1 HBM, 2 shared-memory thread groups, 3 hybrid."""
+        """Which table store the fused kernel runs with: 1 HBM, 2 shared-memory thread groups, 3 hybrid, 4 HBM with a trace
+        agent's sweeps applied lazily (rlb.h: rlb_config.store_kind)."""
         return lib.rlb_engine_store_kind(self.h)
 
     # ---- Agent::train / evaluate
