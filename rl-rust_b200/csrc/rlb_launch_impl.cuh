@@ -111,13 +111,15 @@ cudaError_t launch_run(const Variant& v, const DevParams& p, int store, cudaStre
     const size_t smem = EnvTab<ENV>::smem_bytes(p.S);
     if (store == STORE_LAZY) {   // trace agents, HBM tables, sweeps applied lazily: + the TD history in shared memory
         if (!v.trace) return cudaErrorInvalidValue;
-        const size_t hist = ((smem + 15) & ~(size_t)15) + (size_t)p.lz_cap * kBlock * (v.real == RLB_REAL_F32 ? 4 : 8);
+        constexpr int kLazyBlock = RLB_LZ_BLOCK;
+        const unsigned lz_grid = (unsigned)((p.n_agents + kLazyBlock - 1) / kLazyBlock);
+        const size_t hist = ((smem + 15) & ~(size_t)15) + (size_t)p.lz_cap * kLazyBlock * (v.real == RLB_REAL_F32 ? 4 : 8);
 #define RLB_CALL(R, P, SL, T)                                                                                          \
     if constexpr (T) {                                                                                                 \
         auto kern = k_run<ENV, R, P, SL, true, STORE_LAZY>;                                                            \
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist);          \
         if (err != cudaSuccess) return err;                                                                            \
-        kern<<<grid, kBlock, hist, stream>>>(p);                                                                       \
+        kern<<<lz_grid, kLazyBlock, hist, stream>>>(p);                                                                \
     }
         RLB_VARIANT_SWITCH(v, RLB_CALL)
 #undef RLB_CALL
